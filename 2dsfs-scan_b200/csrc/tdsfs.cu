@@ -1,0 +1,823 @@
+// tdsfs.cu -- C ABI of libtdsfs.so (see include/tdsfs.h) over the kernels in tdsfs_kernels.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tdsfs_kernels.cuh"
+
+using namespace tdsfs;
+
+#define TDSFS_VERSION 100
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) return fail(TDSFS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                            \
+  } while (0)
+#define CKR(call)              \
+  do {                         \
+    int r__ = (call);          \
+    if (r__) return r__;       \
+  } while (0)
+
+enum { EV_BG0, EV_K1, EV_FIN0, EV_FIN1, EV_SC0, EV_K2, EV_K3S, EV_K3L, NEV };
+
+struct Chunk {
+  long long r0, r1;
+  cudaEvent_t ev;
+};
+
+struct tdsfs_ctx {
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+  bool sync = true;
+  // panel
+  int n1 = 0, n2 = 0, fold = 1, R1 = 0, R2 = 0, bins2d = 0;
+  // data
+  long long S = 0;
+  int C = 0;
+  const uint32_t* dG = nullptr;
+  bool own_G = false;
+  int W1 = 0, W2 = 0, ns1 = 0, ns2 = 0;
+  const uint16_t* dCnt = nullptr;
+  bool own_cnt = false;
+  const int32_t* dPos = nullptr;
+  bool own_pos = false;
+  const uint8_t* dFlags = nullptr;
+  bool own_flags = false;
+  tdsfs_fixup_t* dFix = nullptr;
+  long long nfix = 0;
+  std::vector<long long> h_off;
+  std::vector<long long> h_last;  // last position per chromosome (-1 = empty)
+  long long* d_off = nullptr;
+  std::vector<Chunk> chunks;
+  // keys
+  uint32_t* d_key = nullptr;
+  uint32_t* d_alts = nullptr;
+  long long key_cap = 0;
+  bool keys_ready = false;
+  // background
+  int bg_mode = -1, NG = 0;
+  long long gstride = 0;
+  uint32_t* d_hist = nullptr;
+  long long hist_words = 0;
+  int32_t* d_bg_group = nullptr;
+  int32_t* d_score_group = nullptr;
+  bool per_chrom_scoring = false;
+  double *d_lb2 = nullptr, *d_lb1a = nullptr, *d_lb1b = nullptr, *d_B = nullptr, *d_lnI = nullptr;
+  unsigned long long* d_Bsum = nullptr;
+  int table_groups = 0;
+  bool float_bg = false, tables_ready = false;
+  int* d_err = nullptr;
+  // windows / results
+  long long ncand = 0, cand_cap = 0;
+  long long* d_cand_off = nullptr;
+  int32_t *d_wlo = nullptr, *d_whi = nullptr, *d_wchrom = nullptr, *d_large = nullptr;
+  long long *d_wstart = nullptr, *d_wend = nullptr;
+  int* d_nlarge = nullptr;
+  int32_t *r_count = nullptr, *r_n2 = nullptr, *r_n1a = nullptr, *r_n1b = nullptr;
+  double *r_T2 = nullptr, *r_T1a = nullptr, *r_T1b = nullptr;
+  uint8_t* r_flags = nullptr;
+  uint32_t* d_scratch = nullptr;
+  int large_ctas = 0;
+  bool results_ready = false;
+  // instrumentation
+  cudaEvent_t ev[NEV] = {};
+  float ms[8] = {};
+  long long launches = 0;
+};
+
+template <typename T>
+static int dev_alloc(T** p, long long n) {
+  CK(cudaMalloc((void**)p, (size_t)std::max<long long>(n, 1) * sizeof(T)));
+  return 0;
+}
+template <typename T>
+static void dev_free(T*& p) {
+  if (p) cudaFree((void*)p);
+  p = nullptr;
+}
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int finish(tdsfs_ctx* c) {
+  if (c->sync) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ lifetime
+extern "C" const char* tdsfs_last_error(void) { return g_err.c_str(); }
+extern "C" int tdsfs_version(void) { return TDSFS_VERSION; }
+
+extern "C" int tdsfs_create(int device, tdsfs_t** out) {
+  if (!out) return fail(TDSFS_ERR_ARG, "out is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TDSFS_ERR_CUDA, "no CUDA device available: libtdsfs has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(TDSFS_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(TDSFS_ERR_CUDA, "device %s is sm_%d%d; libtdsfs is built for sm_100a only", prop.name, prop.major, prop.minor);
+  tdsfs_ctx* c = new tdsfs_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  for (int i = 0; i < NEV; ++i) CK(cudaEventCreate(&c->ev[i]));
+  CKR(dev_alloc(&c->d_err, 1));
+  CKR(dev_alloc(&c->d_nlarge, 1));
+  CKR(dev_alloc(&c->d_lnI, LN_TABLE));
+  CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  k_ln_int_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_lnI, LN_TABLE);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+static void free_data(tdsfs_ctx* c) {
+  if (c->own_G) { void* p = (void*)c->dG; cudaFree(p); }
+  if (c->own_cnt) { void* p = (void*)c->dCnt; cudaFree(p); }
+  if (c->own_pos) { void* p = (void*)c->dPos; cudaFree(p); }
+  if (c->own_flags) { void* p = (void*)c->dFlags; cudaFree(p); }
+  c->dG = nullptr; c->dCnt = nullptr; c->dPos = nullptr; c->dFlags = nullptr;
+  c->own_G = c->own_cnt = c->own_pos = c->own_flags = false;
+  dev_free(c->dFix);
+  c->nfix = 0;
+  dev_free(c->d_off);
+  for (auto& ch : c->chunks) if (ch.ev) cudaEventDestroy(ch.ev);
+  c->chunks.clear();
+  c->keys_ready = c->tables_ready = c->results_ready = false;
+}
+
+extern "C" void tdsfs_destroy(tdsfs_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_data(c);
+  dev_free(c->d_key); dev_free(c->d_alts); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
+  dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
+  dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
+  dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend); dev_free(c->d_nlarge);
+  dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
+  dev_free(c->r_T1b); dev_free(c->r_flags); dev_free(c->d_scratch);
+  for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->own_stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" int tdsfs_set_stream(tdsfs_t* c, void* s) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return 0;
+}
+
+extern "C" int tdsfs_set_sync(tdsfs_t* c, int sync) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  c->sync = sync != 0;
+  return 0;
+}
+
+extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  if (n1 < 1 || n2 < 1 || n1 > 32767 || n2 > 32767) return fail(TDSFS_ERR_ARG, "panel sizes must be in [1, 32767] (got %d, %d)", n1, n2);
+  long long bins = (long long)(2 * n1 + 1) * (2 * n2 + 1);
+  if (bins >= 0xFFFFFFFFLL) return fail(TDSFS_ERR_ARG, "2D spectrum too large");
+  CK(cudaSetDevice(c->device));
+  c->n1 = n1; c->n2 = n2; c->fold = fold != 0;
+  c->R1 = 2 * n1 + 1; c->R2 = 2 * n2 + 1; c->bins2d = (int)bins;
+  c->keys_ready = c->tables_ready = c->results_ready = false;
+  c->bg_mode = -1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ data
+template <typename T>
+static int adopt_or_upload(tdsfs_ctx* c, const T* src, long long n, const T** dst, bool* own, long long pad_elems = 0) {
+  if (is_device_ptr(src)) {
+    *dst = src;
+    *own = false;
+    return 0;
+  }
+  T* d = nullptr;
+  CKR(dev_alloc(&d, n + pad_elems));
+  CK(cudaMemcpyAsync(d, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  *dst = d;
+  *own = true;
+  return 0;
+}
+
+static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long long* chrom_off, int C, const uint8_t* flags,
+                       bool need_flag_copy) {
+  if (S < 0 || S > 0x7FFFFF00LL) return fail(TDSFS_ERR_ARG, "S = %lld out of range", S);
+  if (C < 1 || !chrom_off || !pos) return fail(TDSFS_ERR_ARG, "pos / chrom_off missing or C < 1");
+  if (chrom_off[0] != 0 || chrom_off[C] != S) return fail(TDSFS_ERR_ARG, "chrom_off must start at 0 and end at S");
+  for (int i = 0; i < C; ++i)
+    if (chrom_off[i + 1] < chrom_off[i]) return fail(TDSFS_ERR_ARG, "chrom_off not monotone");
+  c->S = S;
+  c->C = C;
+  c->h_off.assign(chrom_off, chrom_off + C + 1);
+  CKR(dev_alloc(&c->d_off, C + 1));
+  CK(cudaMemcpyAsync(c->d_off, chrom_off, (size_t)(C + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos));
+  if (flags) {
+    if (need_flag_copy && is_device_ptr(flags)) {
+      uint8_t* d = nullptr;
+      CKR(dev_alloc(&d, S));
+      CK(cudaMemcpyAsync(d, flags, (size_t)S, cudaMemcpyDeviceToDevice, c->stream));
+      c->dFlags = d;
+      c->own_flags = true;
+    } else {
+      CKR(adopt_or_upload(c, flags, S, &c->dFlags, &c->own_flags));
+    }
+  }
+  // last position of every chromosome (sizes the fixed-bp candidate list)
+  c->h_last.assign(C, -1);
+  if (!is_device_ptr(pos)) {
+    for (int i = 0; i < C; ++i)
+      if (chrom_off[i + 1] > chrom_off[i]) c->h_last[i] = pos[chrom_off[i + 1] - 1];
+  } else {
+    for (int i = 0; i < C; ++i)
+      if (chrom_off[i + 1] > chrom_off[i]) {
+        int32_t v;
+        CK(cudaMemcpyAsync(&v, pos + chrom_off[i + 1] - 1, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->h_last[i] = v;
+      }
+  }
+  if (S > c->key_cap) {
+    dev_free(c->d_key);
+    dev_free(c->d_alts);
+    CKR(dev_alloc(&c->d_key, S));
+    CKR(dev_alloc(&c->d_alts, S));
+    c->key_cap = S;
+  }
+  return 0;
+}
+
+extern "C" int tdsfs_load_counts(tdsfs_t* c, const uint16_t* cnt, int64_t S, const int32_t* pos, const int64_t* chrom_off,
+                                 int32_t C, const uint8_t* snp_flags) {
+  if (!c || !cnt) return fail(TDSFS_ERR_ARG, "ctx / cnt is NULL");
+  if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
+  CK(cudaSetDevice(c->device));
+  free_data(c);
+  CKR(load_common(c, S, pos, (const long long*)chrom_off, C, snp_flags, false));
+  CKR(adopt_or_upload(c, cnt, S * 4, &c->dCnt, &c->own_cnt));
+  if (((uintptr_t)c->dCnt & 7) != 0) return fail(TDSFS_ERR_ARG, "cnt must be 8-byte aligned");
+  return finish(c);
+}
+
+extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_t words1, int32_t words2, int32_t ns1,
+                                    int32_t ns2, const int32_t* pos, const int64_t* chrom_off, int32_t C,
+                                    const tdsfs_fixup_t* fixups, int64_t n_fixups, const uint8_t* snp_flags) {
+  if (!c || !G) return fail(TDSFS_ERR_ARG, "ctx / G is NULL");
+  if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
+  if (words1 < 1 || words2 < 1 || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
+    return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d)", words1, words2, ns1, ns2);
+  if ((long long)(words1 + words2) * 512 > 64 * 1024) return fail(TDSFS_ERR_ARG, "row too wide: more than 2048 samples per 128-row tile stage is not supported yet");
+  CK(cudaSetDevice(c->device));
+  free_data(c);
+  const bool has_fix = fixups && n_fixups > 0;
+  CKR(load_common(c, S, pos, (const long long*)chrom_off, C, snp_flags, has_fix));
+  c->W1 = words1; c->W2 = words2; c->ns1 = ns1; c->ns2 = ns2;
+  const long long RW = words1 + words2;
+  if (has_fix) {
+    // flag bit2 marks rows that own fix-ups; build (or extend) the flag array on the host side
+    std::vector<tdsfs_fixup_t> hf(fixups, fixups + n_fixups);
+    if (!std::is_sorted(hf.begin(), hf.end(), [](const tdsfs_fixup_t& a, const tdsfs_fixup_t& b) { return a.snp < b.snp; }))
+      return fail(TDSFS_ERR_ARG, "fixups must be sorted by snp");
+    std::vector<uint8_t> hflags((size_t)S, 3);
+    if (c->dFlags) {
+      CK(cudaMemcpyAsync(hflags.data(), c->dFlags, (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (auto& f : hflags) f &= 3;
+    }
+    for (auto& f : hf) {
+      if (f.snp < 0 || f.snp >= S || (f.pop != 0 && f.pop != 1)) return fail(TDSFS_ERR_ARG, "fixup out of range");
+      hflags[(size_t)f.snp] |= 4;
+    }
+    if (!c->own_flags) {
+      uint8_t* d = nullptr;
+      CKR(dev_alloc(&d, S));
+      c->dFlags = d;
+      c->own_flags = true;
+    }
+    CK(cudaMemcpyAsync((void*)c->dFlags, hflags.data(), (size_t)S, cudaMemcpyHostToDevice, c->stream));
+    CKR(dev_alloc(&c->dFix, n_fixups));
+    CK(cudaMemcpyAsync(c->dFix, hf.data(), (size_t)n_fixups * sizeof(tdsfs_fixup_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->nfix = n_fixups;
+  }
+  if (is_device_ptr(G)) {
+    if (((uintptr_t)G & 15) != 0) return fail(TDSFS_ERR_ARG, "device G must be 16-byte aligned");
+    c->dG = (const uint32_t*)G;
+    c->own_G = false;
+    c->chunks.push_back({0, S, nullptr});
+  } else {
+    // chunked asynchronous upload on the copy stream; tdsfs_background's count kernel consumes chunk by chunk
+    uint32_t* d = nullptr;
+    const long long padded_rows = (S + K1_ROWS - 1) / K1_ROWS * K1_ROWS;
+    CKR(dev_alloc(&d, padded_rows * RW));
+    c->dG = d;
+    c->own_G = true;
+    const long long row_bytes = RW * 4;
+    long long rows_per_chunk = std::max<long long>(K1_ROWS, (64LL << 20) / row_bytes / K1_ROWS * K1_ROWS);
+    CK(cudaStreamSynchronize(c->stream));
+    for (long long r0 = 0; r0 < S; r0 += rows_per_chunk) {
+      const long long r1 = std::min<long long>(S, r0 + rows_per_chunk);
+      Chunk ch{r0, r1, nullptr};
+      CK(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
+      CK(cudaMemcpyAsync(d + r0 * RW, (const uint8_t*)G + r0 * row_bytes, (size_t)((r1 - r0) * row_bytes),
+                         cudaMemcpyHostToDevice, c->copy_stream));
+      CK(cudaEventRecord(ch.ev, c->copy_stream));
+      c->chunks.push_back(ch);
+    }
+    if (S == 0) c->chunks.push_back({0, 0, nullptr});
+  }
+  return finish(c);
+}
+
+// ------------------------------------------------------------------------------------------------ background
+static int ensure_tables(tdsfs_ctx* c, int NG) {
+  if (NG <= c->table_groups) return 0;
+  dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum);
+  CKR(dev_alloc(&c->d_lb2, (long long)NG * c->bins2d));
+  CKR(dev_alloc(&c->d_lb1a, (long long)NG * (c->n1 + 1)));
+  CKR(dev_alloc(&c->d_lb1b, (long long)NG * (c->n2 + 1)));
+  CKR(dev_alloc(&c->d_B, (long long)NG * 3));
+  CKR(dev_alloc(&c->d_Bsum, (long long)NG * 3));
+  c->table_groups = NG;
+  return 0;
+}
+
+static void fill_key_params(tdsfs_ctx* c, KeyParams& p) {
+  memset(&p, 0, sizeof p);
+  p.n1 = c->n1; p.n2 = c->n2; p.fold = c->fold; p.C2 = c->R2; p.bins2d = c->bins2d; p.R1 = c->R1; p.R2 = c->R2;
+  p.ns1 = c->ns1; p.ns2 = c->ns2; p.W1 = c->W1; p.W2 = c->W2;
+  p.S = c->S;
+  p.G = c->dG; p.cnt = c->dCnt; p.pos = c->dPos; p.flags = c->dFlags; p.fix = c->dFix; p.nfix = c->nfix;
+  p.key = c->d_key; p.alts = c->d_alts; p.hist = c->d_hist; p.gstride = c->gstride;
+  p.chrom_off = c->d_off; p.C = c->C; p.err = c->d_err;
+  p.cr = std::min(c->R1, CORNER); p.cc = std::min(c->R2, CORNER);
+  p.h1a = std::min(c->R1, H1CAP); p.h1b = std::min(c->R2, H1CAP);
+}
+
+extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int64_t bg_lo, int64_t bg_hi) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  if (!c->dG && !c->dCnt) return fail(TDSFS_ERR_STATE, "load data first");
+  if (mode < TDSFS_BG_NONE || mode > TDSFS_BG_CHROM) return fail(TDSFS_ERR_ARG, "bad background mode %d", mode);
+  if (mode == TDSFS_BG_CHROM && (bg_chrom < 0 || bg_chrom >= c->C)) return fail(TDSFS_ERR_ARG, "background chromosome %d out of range", bg_chrom);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CK(cudaEventRecord(c->ev[EV_BG0], st));
+  const int NG = mode == TDSFS_BG_PER_CHROM ? c->C : 1;
+  c->gstride = (long long)c->bins2d + c->R1 + c->R2;
+  const long long words = c->gstride * NG;
+  if (words > c->hist_words) {
+    dev_free(c->d_hist);
+    CKR(dev_alloc(&c->d_hist, words));
+    c->hist_words = words;
+  }
+  CK(cudaMemsetAsync(c->d_hist, 0, (size_t)words * 4, st));
+  CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+  c->NG = NG;
+  c->bg_mode = mode;
+  c->float_bg = false;
+  c->tables_ready = false;
+  c->results_ready = false;
+  c->per_chrom_scoring = mode == TDSFS_BG_PER_CHROM;
+
+  KeyParams p;
+  fill_key_params(c, p);
+  p.bg_lo = bg_lo; p.bg_hi = bg_hi;
+  if (bg_lo < 0 || bg_hi < 0) { p.bg_lo = -1; p.bg_hi = -1; }
+  p.bg_group = nullptr;
+  p.uniform_group = mode == TDSFS_BG_GENOME ? 0 : -1;
+  if (mode == TDSFS_BG_PER_CHROM || mode == TDSFS_BG_CHROM) {
+    std::vector<int32_t> g(c->C);
+    for (int i = 0; i < c->C; ++i) g[i] = mode == TDSFS_BG_PER_CHROM ? i : (i == bg_chrom ? 0 : -1);
+    dev_free(c->d_bg_group);
+    CKR(dev_alloc(&c->d_bg_group, c->C));
+    CK(cudaMemcpyAsync(c->d_bg_group, g.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // g is a stack-lifetime buffer
+    p.bg_group = c->d_bg_group;
+  }
+  if (mode == TDSFS_BG_PER_CHROM) {
+    std::vector<int32_t> g(c->C);
+    for (int i = 0; i < c->C; ++i) g[i] = i;
+    dev_free(c->d_score_group);
+    CKR(dev_alloc(&c->d_score_group, c->C));
+    CK(cudaMemcpyAsync(c->d_score_group, g.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+
+  const int hist_bytes = (p.cr * p.cc + p.h1a + p.h1b) * 4;
+  if (c->dG) {
+    const int RW = c->W1 + c->W2;
+    p.stage_bytes = K1_ROWS * RW * 4;
+    int nstage = std::max(2, std::min(8, (96 * 1024) / p.stage_bytes));
+    p.nstage = nstage;
+    const int smem = nstage * p.stage_bytes + nstage * 16 + hist_bytes;
+    const bool aligned = (c->W1 % 4 == 0) && (c->W2 % 4 == 0);
+    auto kern = aligned ? k1_genotypes<true> : k1_genotypes<false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
+    occ = std::max(1, occ);
+    for (auto& ch : c->chunks) {
+      if (ch.r1 <= ch.r0) continue;
+      if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
+      p.r0 = ch.r0; p.r1 = ch.r1;
+      const long long ntiles = (ch.r1 - ch.r0 + K1_ROWS - 1) / K1_ROWS;
+      const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count * occ);
+      kern<<<grid, K1_THREADS, smem, st>>>(p);
+      c->launches++;
+    }
+  } else {
+    p.r0 = 0; p.r1 = c->S;
+    const long long ntiles = (c->S + K1C_THREADS - 1) / K1C_THREADS;
+    if (ntiles > 0) {
+      CK(cudaFuncSetAttribute(k1_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_bytes));
+      const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count * 4);
+      k1_counts<<<grid, K1C_THREADS, hist_bytes, st>>>(p);
+      c->launches++;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev[EV_K1], st));
+  c->keys_ready = true;
+  CKR(finish(c));
+  if (c->sync) {
+    int err = 0;
+    CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err & 1) {
+      c->keys_ready = false;
+      return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
+    }
+    cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
+    c->ms[5] = c->ms[0];
+  }
+  return 0;
+}
+
+extern "C" int tdsfs_background_device(tdsfs_t* c, void** dev_ptr, int64_t* n_words, int32_t* n_groups) {
+  if (!c || !c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (dev_ptr) *dev_ptr = c->d_hist;
+  if (n_words) *n_words = c->gstride * c->NG;
+  if (n_groups) *n_groups = c->NG;
+  return 0;
+}
+
+extern "C" int tdsfs_get_background(tdsfs_t* c, int32_t group, uint64_t* s2, uint64_t* s1a, uint64_t* s1b) {
+  if (!c || !c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (group < 0 || group >= c->NG) return fail(TDSFS_ERR_ARG, "group %d out of range", group);
+  CK(cudaSetDevice(c->device));
+  std::vector<uint32_t> h((size_t)c->gstride);
+  CK(cudaMemcpyAsync(h.data(), c->d_hist + (long long)group * c->gstride, (size_t)c->gstride * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (s2) for (int i = 0; i < c->bins2d; ++i) s2[i] = h[i];
+  if (s1a) for (int i = 0; i < c->R1; ++i) s1a[i] = h[c->bins2d + i];
+  if (s1b) for (int i = 0; i < c->R2; ++i) s1b[i] = h[c->bins2d + c->R1 + i];
+  return 0;
+}
+
+extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double* b1a, const double* b1b) {
+  if (!c || !b2d || !b1a || !b1b) return fail(TDSFS_ERR_ARG, "NULL argument");
+  if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CKR(ensure_tables(c, 1));
+  // interior totals summed on the host in index order, as the reference's sum(counts_bg) does (:665, :517)
+  double B[3] = {0, 0, 0};
+  for (int k = 1; k < c->bins2d - 1; ++k) B[0] += b2d[k];
+  for (int k = 1; k <= c->n1 - 1; ++k) B[1] += b1a[k];
+  for (int k = 1; k <= c->n2 - 1; ++k) B[2] += b1b[k];
+  double *t2 = nullptr, *t1a = nullptr, *t1b = nullptr;
+  CKR(dev_alloc(&t2, c->bins2d)); CKR(dev_alloc(&t1a, c->n1 + 1)); CKR(dev_alloc(&t1b, c->n2 + 1));
+  CK(cudaMemcpyAsync(t2, b2d, (size_t)c->bins2d * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(t1a, b1a, (size_t)(c->n1 + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(t1b, b1b, (size_t)(c->n2 + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_B, B, sizeof B, cudaMemcpyHostToDevice, st));
+  k_log_table<<<std::min(1024, (c->bins2d + 255) / 256), 256, 0, st>>>(t2, c->d_lb2, c->bins2d);
+  k_log_table<<<1, 256, 0, st>>>(t1a, c->d_lb1a, c->n1 + 1);
+  k_log_table<<<1, 256, 0, st>>>(t1b, c->d_lb1b, c->n2 + 1);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  cudaFree(t2); cudaFree(t1a); cudaFree(t1b);
+  c->float_bg = true;
+  c->per_chrom_scoring = false;
+  c->tables_ready = true;
+  c->results_ready = false;
+  return 0;
+}
+
+extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  if (c->float_bg) return 0;  // tables were built by tdsfs_set_background
+  if (!c->keys_ready || c->bg_mode == TDSFS_BG_NONE) return fail(TDSFS_ERR_STATE, "no integer background to finalize");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CK(cudaEventRecord(c->ev[EV_FIN0], st));
+  CKR(ensure_tables(c, c->NG));
+  CK(cudaMemsetAsync(c->d_Bsum, 0, (size_t)c->NG * 3 * 8, st));
+  FinParams f;
+  f.hist = c->d_hist; f.gstride = c->gstride; f.NG = c->NG; f.bins2d = c->bins2d; f.R1 = c->R1; f.R2 = c->R2;
+  f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum;
+  dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 4, (c->bins2d + 255) / 256)), (unsigned)c->NG);
+  k_finalize_counts<<<grid, 256, 0, st>>>(f);
+  k_u64_to_double<<<(c->NG * 3 + 255) / 256, 256, 0, st>>>(c->d_Bsum, c->d_B, c->NG * 3);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev[EV_FIN1], st));
+  c->tables_ready = true;
+  CKR(finish(c));
+  if (c->sync) cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ scans
+static int candidates(tdsfs_ctx* c, long long W, bool snp_mode, std::vector<long long>& off) {
+  off.assign(c->C + 1, 0);
+  for (int i = 0; i < c->C; ++i) {
+    long long n = 0;
+    const long long sc = c->h_off[i + 1] - c->h_off[i];
+    if (sc > 0) n = snp_mode ? sc / W : (std::max<long long>(c->h_last[i] - 1, 0) / W + 1);
+    off[i + 1] = off[i] + n;
+  }
+  if (off[c->C] > 0x7FFFFFF0LL) return fail(TDSFS_ERR_ARG, "too many candidate windows (%lld)", off[c->C]);
+  return 0;
+}
+
+extern "C" int tdsfs_candidates_bp(tdsfs_t* c, int64_t W, int64_t* n) {
+  if (!c || !n || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!c->dPos) return fail(TDSFS_ERR_STATE, "load data first");
+  std::vector<long long> off;
+  CKR(candidates(c, W, false, off));
+  *n = off[c->C];
+  return 0;
+}
+extern "C" int tdsfs_candidates_snp(tdsfs_t* c, int64_t N, int64_t* n) {
+  if (!c || !n || N < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!c->dPos) return fail(TDSFS_ERR_STATE, "load data first");
+  std::vector<long long> off;
+  CKR(candidates(c, N, true, off));
+  *n = off[c->C];
+  return 0;
+}
+
+static int ensure_windows(tdsfs_ctx* c, long long n) {
+  if (n <= c->cand_cap) return 0;
+  dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom); dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend);
+  dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
+  dev_free(c->r_T1b); dev_free(c->r_flags);
+  CKR(dev_alloc(&c->d_wlo, n)); CKR(dev_alloc(&c->d_whi, n)); CKR(dev_alloc(&c->d_wchrom, n)); CKR(dev_alloc(&c->d_large, n));
+  CKR(dev_alloc(&c->d_wstart, n)); CKR(dev_alloc(&c->d_wend, n));
+  CKR(dev_alloc(&c->r_count, n)); CKR(dev_alloc(&c->r_n2, n)); CKR(dev_alloc(&c->r_n1a, n)); CKR(dev_alloc(&c->r_n1b, n));
+  CKR(dev_alloc(&c->r_T2, n)); CKR(dev_alloc(&c->r_T1a, n)); CKR(dev_alloc(&c->r_T1b, n)); CKR(dev_alloc(&c->r_flags, n));
+  c->cand_cap = n;
+  return 0;
+}
+
+extern "C" int tdsfs_fetch_results(tdsfs_t* c, tdsfs_result_t* out, int64_t cap, int64_t* n_windows) {
+  if (!c || !out) return fail(TDSFS_ERR_ARG, "NULL argument");
+  if (!c->results_ready) return fail(TDSFS_ERR_STATE, "no scan results");
+  if (cap < c->ncand) return fail(TDSFS_ERR_ARG, "result capacity %lld < %lld candidate windows", (long long)cap, c->ncand);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const size_t n = (size_t)c->ncand;
+#define D2H(dst, src, T) \
+  if (out->dst && n) CK(cudaMemcpyAsync(out->dst, c->src, n * sizeof(T), cudaMemcpyDeviceToHost, st))
+  D2H(chrom, d_wchrom, int32_t);
+  D2H(start, d_wstart, long long);
+  D2H(end, d_wend, long long);
+  D2H(snp_count, r_count, int32_t);
+  D2H(n2d, r_n2, int32_t);
+  D2H(n1d_p1, r_n1a, int32_t);
+  D2H(n1d_p2, r_n1b, int32_t);
+  D2H(T2D, r_T2, double);
+  D2H(T1D_p1, r_T1a, double);
+  D2H(T1D_p2, r_T1b, double);
+  D2H(flags, r_flags, uint8_t);
+#undef D2H
+  CK(cudaStreamSynchronize(st));
+  if (n_windows) *n_windows = c->ncand;
+  return 0;
+}
+
+static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, int64_t cap, int64_t* n_windows) {
+  if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  std::vector<long long> off;
+  CKR(candidates(c, W, snp_mode, off));
+  const long long ncand = off[c->C];
+  if (out && cap < ncand) return fail(TDSFS_ERR_ARG, "result capacity %lld < %lld candidate windows", (long long)cap, ncand);
+  CKR(ensure_windows(c, ncand));
+  dev_free(c->d_cand_off);
+  CKR(dev_alloc(&c->d_cand_off, c->C + 1));
+  CK(cudaMemcpyAsync(c->d_cand_off, off.data(), (size_t)(c->C + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // `off` is a local buffer
+  CK(cudaEventRecord(c->ev[EV_SC0], st));
+  c->ncand = ncand;
+  if (ncand > 0) {
+    CK(cudaMemsetAsync(c->d_nlarge, 0, sizeof(int), st));
+    WinParams w;
+    w.pos = c->dPos; w.chrom_off = c->d_off; w.cand_off = c->d_cand_off; w.C = c->C; w.W = W; w.ncand = ncand;
+    w.wlo = c->d_wlo; w.whi = c->d_whi; w.wchrom = c->d_wchrom; w.wstart = c->d_wstart; w.wend = c->d_wend;
+    w.large = c->d_large; w.nlarge = c->d_nlarge;
+    const int g2 = (int)((ncand + 255) / 256);
+    if (snp_mode) k2_bounds_snp<<<g2, 256, 0, st>>>(w); else k2_bounds_bp<<<g2, 256, 0, st>>>(w);
+    c->launches++;
+    CK(cudaEventRecord(c->ev[EV_K2], st));
+
+    ScoreParams s;
+    memset(&s, 0, sizeof s);
+    s.key = c->d_key; s.alts = c->d_alts; s.flags = c->dFlags; s.wlo = c->d_wlo; s.whi = c->d_whi; s.wchrom = c->d_wchrom;
+    s.score_group = c->per_chrom_scoring ? c->d_score_group : nullptr;
+    s.ncand = ncand; s.n1 = c->n1; s.n2 = c->n2; s.bins2d = c->bins2d; s.snp_mode = snp_mode;
+    s.lb2 = c->d_lb2; s.lb1a = c->d_lb1a; s.lb1b = c->d_lb1b; s.B = c->d_B; s.lnI = c->d_lnI;
+    s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
+    s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
+    // small windows: one warp each
+    const int wwords = score_warp_smem_words(c->n1, c->n2);
+    int warps = std::min(SCORE_WARPS, (200 * 1024) / (wwords * 4));
+    if (warps < 1) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer");
+    const int smem = warps * wwords * 4;
+    CK(cudaFuncSetAttribute(k3_score_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_score_small, SCORE_WARPS * 32, smem));
+    occ = std::max(1, occ);
+    const long long want = (ncand + warps - 1) / warps;
+    const int grid = (int)std::min<long long>(want, (long long)c->sm_count * occ);
+    k3_score_small<<<grid, SCORE_WARPS * 32, smem, st>>>(s, warps);
+    c->launches++;
+    CK(cudaEventRecord(c->ev[EV_K3S], st));
+    // large windows: one CTA each over dense global scratch
+    const long long sstride = (long long)c->bins2d + c->n1 + 1 + c->n2 + 1;
+    if (!c->d_scratch) {
+      c->large_ctas = (int)std::max<long long>(8, std::min<long long>(2 * c->sm_count, (256LL << 20) / (sstride * 4)));
+      CKR(dev_alloc(&c->d_scratch, sstride * c->large_ctas));
+      CK(cudaMemsetAsync(c->d_scratch, 0, (size_t)(sstride * c->large_ctas) * 4, st));
+    }
+    s.scratch = c->d_scratch;
+    k3_score_large<<<c->large_ctas, LARGE_THREADS, 0, st>>>(s);
+    c->launches++;
+    CK(cudaEventRecord(c->ev[EV_K3L], st));
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaEventRecord(c->ev[EV_K2], st));
+    CK(cudaEventRecord(c->ev[EV_K3S], st));
+    CK(cudaEventRecord(c->ev[EV_K3L], st));
+  }
+  c->results_ready = true;
+  if (out) {
+    CKR(tdsfs_fetch_results(c, out, cap, n_windows));
+  } else {
+    if (n_windows) *n_windows = ncand;
+    CKR(finish(c));
+  }
+  if (c->sync || out) {
+    cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
+    cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
+    cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
+    cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);
+  }
+  return 0;
+}
+
+extern "C" int tdsfs_scan_bp(tdsfs_t* c, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, W, false, out, cap, n); }
+extern "C" int tdsfs_scan_snp(tdsfs_t* c, int64_t N, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, N, true, out, cap, n); }
+
+extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  const bool was_sync = c->sync;
+  c->sync = false;  // one synchronisation at the end of the whole pass
+  int r = tdsfs_background(c, bg_mode, 0, -1, -1);
+  if (!r) r = tdsfs_finalize_background(c);
+  if (!r) r = scan(c, W, false, out, cap, n);
+  c->sync = was_sync;
+  if (r) return r;
+  CK(cudaStreamSynchronize(c->stream));
+  int err = 0;
+  CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
+  if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
+  cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
+  cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
+  cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
+  cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
+  cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
+  cudaEventElapsedTime(&c->ms[5], c->ev[EV_BG0], c->ev[EV_K1]);
+  cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);
+  cudaEventElapsedTime(&c->ms[7], c->ev[EV_BG0], c->ev[EV_K3L]);
+  return 0;
+}
+
+extern "C" int tdsfs_window_spectra(tdsfs_t* c, int64_t window, uint64_t* s2, uint64_t* s1a, uint64_t* s1b) {
+  if (!c || !c->results_ready) return fail(TDSFS_ERR_STATE, "scan first");
+  if (window < 0 || window >= c->ncand) return fail(TDSFS_ERR_ARG, "window %lld out of range", (long long)window);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  int32_t lo, hi;
+  CK(cudaMemcpyAsync(&lo, c->d_wlo + window, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hi, c->d_whi + window, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const long long words = (long long)c->bins2d + c->R1 + c->R2;
+  uint32_t* d = nullptr;
+  CKR(dev_alloc(&d, words));
+  CK(cudaMemsetAsync(d, 0, (size_t)words * 4, st));
+  if (hi > lo) {
+    k_window_hist<<<std::min(1024, (hi - lo + 255) / 256), 256, 0, st>>>(c->d_key, c->d_alts, lo, hi, d, d + c->bins2d, d + c->bins2d + c->R1);
+    c->launches++;
+  }
+  std::vector<uint32_t> h((size_t)words);
+  CK(cudaMemcpyAsync(h.data(), d, (size_t)words * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  if (s2) for (int i = 0; i < c->bins2d; ++i) s2[i] = h[i];
+  if (s1a) for (int i = 0; i < c->R1; ++i) s1a[i] = h[c->bins2d + i];
+  if (s1b) for (int i = 0; i < c->R2; ++i) s1b[i] = h[c->bins2d + c->R1 + i];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ explicit likelihood
+extern "C" int tdsfs_likelihood(tdsfs_t* c, const int64_t* x, const double* b, int64_t n, double B, double* T, int32_t* flag) {
+  if (!c || !T || !flag || n < 0 || (n > 0 && (!x || !b))) return fail(TDSFS_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  long long* dx = nullptr;
+  double *db = nullptr, *dout = nullptr;
+  int* dflag = nullptr;
+  CKR(dev_alloc(&dx, n)); CKR(dev_alloc(&db, n)); CKR(dev_alloc(&dout, 1)); CKR(dev_alloc(&dflag, 1));
+  if (n) {
+    CK(cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db, b, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  }
+  k_likelihood<<<1, 256, 0, st>>>(dx, db, n, B, dout, dflag);
+  c->launches++;
+  CK(cudaGetLastError());
+  int hf = 0;
+  CK(cudaMemcpyAsync(T, dout, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hf, dflag, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *flag = hf;
+  cudaFree(dx); cudaFree(db); cudaFree(dout); cudaFree(dflag);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic + instrumentation
+extern "C" int tdsfs_synth_genotypes(tdsfs_t* c, void* G_dev, int64_t S, int64_t snp0, int32_t words1, int32_t words2,
+                                     int32_t ns1, int32_t ns2, uint64_t seed, double missing_rate, double fst) {
+  if (!c || !G_dev || S < 0) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!is_device_ptr(G_dev)) return fail(TDSFS_ERR_ARG, "G_dev must be device memory");
+  CK(cudaSetDevice(c->device));
+  const long long total = S * (long long)(words1 + words2);
+  const uint32_t thr = (uint32_t)(missing_rate * 65536.0);
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 0x7FFFFFFFLL) return fail(TDSFS_ERR_ARG, "matrix too large for one launch");
+  if (blocks) {
+    k_synth<<<(unsigned)blocks, 256, 0, c->stream>>>((uint32_t*)G_dev, S, snp0, words1, words2, ns1, ns2, seed, thr, fst);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
+  if (!c || !ms) return fail(TDSFS_ERR_ARG, "NULL argument");
+  for (int i = 0; i < n && i < 8; ++i) ms[i] = c->ms[i];
+  return 0;
+}
+
+extern "C" int64_t tdsfs_launch_count(tdsfs_t* c) { return c ? c->launches : 0; }

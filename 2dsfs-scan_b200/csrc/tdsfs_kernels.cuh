@@ -1,0 +1,913 @@
+// tdsfs_kernels.cuh -- hand-written sm_100a kernels of the 2DSFS-scan hot path.
+//
+// Reference code replaced (paths relative to uricchio/2DSFS-scan):
+//   K1  count kernel        scripts/src/twoDSFS_class.py:118-130 (per-sample ref/alt counting),
+//                           :190-217 (joint fold, skip, 2D bin), :427-433 (raw 1D alt count)
+//   K2  window boundaries   :843-949 (fixed-bp walk), :1515-1535 (fixed-SNP walk)
+//   K3  window spectra      :140-232, :398-463 applied to window_data
+//   K4  fused scores        :478-537, :625-684 (scipy multinomial.logpmf difference)
+//
+// All integer work is exact; likelihoods are fp64.  No tensor cores (nothing here is a contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/tdsfs.h"
+
+namespace tdsfs {
+
+// ------------------------------------------------------------------------------------------------ constants
+constexpr int K1_ROWS = 128;          // rows per TMA tile == consumer threads of the genotype count kernel
+constexpr int K1_THREADS = K1_ROWS + 32;  // + one producer warp
+constexpr int CORNER = 64;            // privatised low-count corner of the 2D background histogram (per CTA, smem)
+constexpr int H1CAP = 2048;           // privatised 1D bins per population (per CTA, smem)
+constexpr int HASH_SLOTS = 1024;      // per-warp open-addressing table of the window scorer
+constexpr int WCAP = 768;             // windows up to WCAP SNPs are scored by one warp; larger ones by a CTA
+constexpr int LN_TABLE = 4096;        // ln(m) lookup for window multiplicities
+constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
+
+struct KeyParams {
+  int n1, n2, fold, C2, bins2d, R1, R2;   // R1 = 2n1+1, R2 = C2 = 2n2+1
+  int ns1, ns2, W1, W2;                   // sample columns and uint32 words per population block
+  long long S, r0, r1;                    // total rows; row range of this launch
+  const uint32_t* G;
+  const uint16_t* cnt;
+  const int32_t* pos;
+  const uint8_t* flags;
+  const tdsfs_fixup_t* fix;
+  long long nfix;
+  uint32_t* key;      // folded 2D bin index a1'*(2n2+1)+a2'; 0 = contributes nothing
+  uint32_t* alts;     // raw alt1 | raw alt2 << 16 (0 when filtered out)
+  uint32_t* hist;     // [group][bins2d | R1 | R2]
+  long long gstride;
+  const int32_t* bg_group;  // per chromosome -> background group, -1 = not in any background; NULL = uniform_group
+  int uniform_group;        // used when bg_group == NULL (0 = genome-wide, -1 = no background)
+  const long long* chrom_off;
+  int C;
+  long long bg_lo, bg_hi;   // optional position restriction of the background (-1 = none)
+  int* err;                 // bit0: count out of range
+  int cr, cc;               // corner dims actually used: min(R1, CORNER), min(R2, CORNER)
+  int h1a, h1b;             // privatised 1D bins: min(R1, H1CAP), min(R2, H1CAP)
+  int nstage, stage_bytes;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// carry-save adder on 32 independent bit lanes: (hi, lo) = a + b + c
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t l = a ^ b ^ c;                    // one LOP3 (0x96)
+  const uint32_t h = (a & b) | (c & (a | b));      // one LOP3 (0xE8, majority)
+  hi = h;
+  lo = l;
+}
+
+// Bit-sliced population counter (Harley-Seal): total() = sum of popcounts of every word added.
+struct BitCounter {
+  uint32_t ones = 0, twos = 0, fours = 0, acc8 = 0;
+  __device__ __forceinline__ void add8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                       uint32_t w6, uint32_t w7) {
+    uint32_t t0, t1, t2, t3, f0, f1, e0;
+    csa(t0, ones, ones, w0, w1);
+    csa(t1, ones, ones, w2, w3);
+    csa(t2, ones, ones, w4, w5);
+    csa(t3, ones, ones, w6, w7);
+    csa(f0, twos, twos, t0, t1);
+    csa(f1, twos, twos, t2, t3);
+    csa(e0, fours, fours, f0, f1);
+    acc8 += __popc(e0);
+  }
+  __device__ __forceinline__ void add4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint32_t t0, t1, f0;
+    csa(t0, ones, ones, w0, w1);
+    csa(t1, ones, ones, w2, w3);
+    csa(f0, twos, twos, t0, t1);
+    uint32_t c = fours & f0;
+    fours ^= f0;
+    acc8 += __popc(c);
+  }
+  __device__ __forceinline__ void add2(uint32_t w0, uint32_t w1) {
+    uint32_t t0;
+    csa(t0, ones, ones, w0, w1);
+    uint32_t c = twos & t0;
+    twos ^= t0;
+    uint32_t c2 = fours & c;
+    fours ^= c;
+    acc8 += __popc(c2);
+  }
+  __device__ __forceinline__ uint32_t total() const {
+    return 8u * acc8 + 4u * __popc(fours) + 2u * __popc(twos) + __popc(ones);
+  }
+};
+
+// Two words' MISSING planes packed into one word: code 0b10 = missing -> bit (hi & ~lo).
+// wa's flags land on even bit positions, wb's on odd positions.
+__device__ __forceinline__ uint32_t pack_missing(uint32_t wa, uint32_t wb) {
+  uint32_t fa = (wa >> 1) & ~wa;  // valid at even bits
+  uint32_t fb = wb & ~(wb << 1);  // valid at odd bits
+  return (fa & 0x55555555u) | (fb & 0xAAAAAAAAu);  // one LOP3
+}
+
+// Per-population accumulation over one row block held in shared memory.
+// alt = popcount(all bits) - #missing   (codes 00 -> 0, 01 -> 1, 11 -> 2, 10 = missing -> popcount 1, removed)
+struct PopCounts {
+  BitCounter bits, miss;
+  __device__ __forceinline__ void chunk4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    bits.add4(w0, w1, w2, w3);
+    miss.add2(pack_missing(w0, w1), pack_missing(w2, w3));
+  }
+  __device__ __forceinline__ void chunk8(uint4 a, uint4 b) {
+    bits.add8(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+    miss.add4(pack_missing(a.x, a.y), pack_missing(a.z, a.w), pack_missing(b.x, b.y), pack_missing(b.z, b.w));
+  }
+};
+
+// words of one population block, 16-byte aligned in smem, nchunk = W/4 chunks, bank-rotated start `rot`
+__device__ __forceinline__ void count_block_aligned(const uint4* blk, int nchunk, int rot, uint32_t& T, uint32_t& M) {
+  PopCounts pc;
+  int c = rot;  // rot < nchunk guaranteed by the caller
+  int i = 0;
+  for (; i + 2 <= nchunk; i += 2) {
+    uint4 a = blk[c];
+    c = (c + 1 == nchunk) ? 0 : c + 1;
+    uint4 b = blk[c];
+    c = (c + 1 == nchunk) ? 0 : c + 1;
+    pc.chunk8(a, b);
+  }
+  if (i < nchunk) {
+    uint4 a = blk[c];
+    pc.chunk4(a.x, a.y, a.z, a.w);
+  }
+  T = pc.bits.total();
+  M = pc.miss.total();
+}
+
+// generic: W words, 4-byte aligned
+__device__ __forceinline__ void count_block_words(const uint32_t* blk, int W, uint32_t& T, uint32_t& M) {
+  PopCounts pc;
+  int i = 0;
+  for (; i + 8 <= W; i += 8) {
+    uint4 a = make_uint4(blk[i], blk[i + 1], blk[i + 2], blk[i + 3]);
+    uint4 b = make_uint4(blk[i + 4], blk[i + 5], blk[i + 6], blk[i + 7]);
+    pc.chunk8(a, b);
+  }
+  for (; i < W; i += 4) {
+    uint32_t w0 = blk[i];
+    uint32_t w1 = (i + 1 < W) ? blk[i + 1] : 0u;
+    uint32_t w2 = (i + 2 < W) ? blk[i + 2] : 0u;
+    uint32_t w3 = (i + 3 < W) ? blk[i + 3] : 0u;
+    pc.chunk4(w0, w1, w2, w3);
+  }
+  T = pc.bits.total();
+  M = pc.miss.total();
+}
+
+// ------------------------------------------------------------------------------------------------ row sink
+// Shared-memory privatised background histograms of ONE background group per CTA.
+struct SinkSmem {
+  uint32_t* corner;  // [cr*cc]
+  uint32_t* h1a;     // [h1a]
+  uint32_t* h1b;     // [h1b]
+};
+
+struct ChromCache {
+  int c = -1;
+  long long lo = 0, hi = -1;
+};
+
+__device__ __forceinline__ int chrom_of_row(const KeyParams& p, long long s, ChromCache& cc) {
+  if (s >= cc.lo && s < cc.hi) return cc.c;
+  int lo = 0, hi = p.C;  // find c with off[c] <= s < off[c+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(p.chrom_off + mid) <= s) lo = mid; else hi = mid;
+  }
+  cc.c = lo;
+  cc.lo = __ldg(p.chrom_off + lo);
+  cc.hi = __ldg(p.chrom_off + lo + 1);
+  return lo;
+}
+
+__device__ __forceinline__ int group_of_row(const KeyParams& p, long long s, ChromCache& cc) {
+  int g = p.uniform_group;
+  if (p.bg_group) g = __ldg(p.bg_group + chrom_of_row(p, s, cc));
+  if (g >= 0 && p.bg_lo >= 0) {
+    long long q = __ldg(p.pos + s);
+    if (q < p.bg_lo || q > p.bg_hi) g = -1;
+  }
+  return g;
+}
+
+// From the four counts of a SNP to its keys, the output arrays and the background histograms.
+__device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int ref1, int alt1, int ref2, int alt2, int cta_group,
+                                         const SinkSmem& sm, ChromCache& cc) {
+  bool include = true;
+  if (p.flags) {
+    uint8_t f = __ldg(p.flags + s);
+    include = (f & 1) != 0;
+    if (f & 4) {  // sparse half-call corrections: binary search the sorted fix-up list
+      long long lo = 0, hi = p.nfix;
+      while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (p.fix[mid].snp < s) lo = mid + 1; else hi = mid;
+      }
+      for (; lo < p.nfix && p.fix[lo].snp == s; ++lo) {
+        if (p.fix[lo].pop == 0) { ref1 += p.fix[lo].dref; alt1 += p.fix[lo].dalt; }
+        else { ref2 += p.fix[lo].dref; alt2 += p.fix[lo].dalt; }
+      }
+    }
+  }
+  uint32_t key = 0, alts = 0;
+  if (include) {
+    int k1 = alt1, k2 = alt2;
+    if (p.fold && alt1 + alt2 > p.n1 + p.n2) { k1 = ref1; k2 = ref2; }  // twoDSFS_class.py:199-206
+    if ((unsigned)k1 >= (unsigned)p.R1 || (unsigned)k2 >= (unsigned)p.R2 || (unsigned)alt1 >= (unsigned)p.R1 ||
+        (unsigned)alt2 >= (unsigned)p.R2) {
+      atomicOr(p.err, 1);
+    } else {
+      key = (uint32_t)(k1 * p.C2 + k2);  // (0,0) -> 0 : skipped SNP (:212)
+      alts = (uint32_t)alt1 | ((uint32_t)alt2 << 16);
+      int g = group_of_row(p, s, cc);
+      if (g >= 0) {
+        uint32_t* gh = p.hist + (long long)g * p.gstride;
+        if (key) {
+          if (g == cta_group && k1 < p.cr && k2 < p.cc) atomicAdd(sm.corner + k1 * p.cc + k2, 1u);
+          else atomicAdd(gh + key, 1u);
+        }
+        if (alt1) {
+          if (g == cta_group && alt1 < p.h1a) atomicAdd(sm.h1a + alt1, 1u);
+          else atomicAdd(gh + p.bins2d + alt1, 1u);
+        }
+        if (alt2) {
+          if (g == cta_group && alt2 < p.h1b) atomicAdd(sm.h1b + alt2, 1u);
+          else atomicAdd(gh + p.bins2d + p.R1 + alt2, 1u);
+        }
+      }
+    }
+  }
+  p.key[s] = key;
+  p.alts[s] = alts;
+}
+
+// flush the CTA-private histograms of group g into global memory (threads tid..nthr of the sink group)
+__device__ __forceinline__ void sink_flush(const KeyParams& p, const SinkSmem& sm, int g, int tid, int nthr) {
+  if (g < 0) return;
+  uint32_t* gh = p.hist + (long long)g * p.gstride;
+  for (int i = tid; i < p.cr * p.cc; i += nthr) {
+    uint32_t v = sm.corner[i];
+    if (v) {
+      atomicAdd(gh + (i / p.cc) * p.C2 + (i % p.cc), v);
+      sm.corner[i] = 0;
+    }
+  }
+  for (int i = tid; i < p.h1a; i += nthr) {
+    uint32_t v = sm.h1a[i];
+    if (v) { atomicAdd(gh + p.bins2d + i, v); sm.h1a[i] = 0; }
+  }
+  for (int i = tid; i < p.h1b; i += nthr) {
+    uint32_t v = sm.h1b[i];
+    if (v) { atomicAdd(gh + p.bins2d + p.R1 + i, v); sm.h1b[i] = 0; }
+  }
+}
+
+__device__ __forceinline__ int tile_group(const KeyParams& p, long long row0, ChromCache& cc) {
+  if (!p.bg_group) return p.uniform_group;
+  return __ldg(p.bg_group + chrom_of_row(p, row0, cc));
+}
+
+// ------------------------------------------------------------------------------------------------ K1 (genotypes)
+// Persistent CTAs; warp 4 = TMA producer streaming 128-row tiles of the genotype matrix into a shared-memory ring
+// (cp.async.bulk + mbarrier), warps 0-3 = consumers, one SNP row per thread: bit-sliced popcount of the row's
+// two population blocks, fold/key, coalesced key stores, privatised background histograms.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(K1_THREADS) k1_genotypes(const __grid_constant__ KeyParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int RW = p.W1 + p.W2;
+  uint8_t* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
+  uint64_t* empty = full + p.nstage;
+  SinkSmem sm;
+  sm.corner = reinterpret_cast<uint32_t*>(empty + p.nstage);
+  sm.h1a = sm.corner + p.cr * p.cc;
+  sm.h1b = sm.h1a + p.h1a;
+  const int nhist = p.cr * p.cc + p.h1a + p.h1b;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, K1_ROWS);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
+  __syncthreads();
+
+  // contiguous tile range of this CTA
+  const long long ntiles = (p.r1 - p.r0 + K1_ROWS - 1) / K1_ROWS;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x;
+  const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const uint32_t tile_bytes = (uint32_t)p.stage_bytes;
+
+  if (tid >= K1_ROWS) {
+    // ---------------- producer warp ----------------
+    if (tid == K1_ROWS) {
+      long long i = 0;
+      for (long long t = t0; t < t1; ++t, ++i) {
+        const int st = (int)(i % p.nstage);
+        if (i >= p.nstage) mbar_wait(empty + st, (uint32_t)(((i / p.nstage) - 1) & 1));
+        const long long row0 = p.r0 + t * K1_ROWS;
+        if (row0 + K1_ROWS <= p.S) {
+          mbar_arrive_expect_tx(full + st, tile_bytes);
+          bulk_g2s(stages + (size_t)st * p.stage_bytes, p.G + row0 * RW, tile_bytes, full + st);
+        } else {
+          mbar_arrive(full + st);  // ragged last tile: consumers fetch their own rows
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  ChromCache cc;
+  int cta_group = -2;
+  // bank rotation for conflict-free 16-byte shared loads (DESIGN.md "K1 shared-memory access")
+  int rot1 = 0, rot2 = 0;
+  if (ALIGNED) {
+    const int rc = RW >> 2;  // 16-byte chunks per row
+    int k = 0;
+    while (k < 3 && ((rc >> k) & 1) == 0) ++k;
+    const int rot = (tid & 7) >> (3 - k);
+    rot1 = rot % (p.W1 >> 2);
+    rot2 = rot % (p.W2 >> 2);
+  }
+  long long i = 0;
+  for (long long t = t0; t < t1; ++t, ++i) {
+    const int st = (int)(i % p.nstage);
+    const long long row0 = p.r0 + t * K1_ROWS;
+    const long long s = row0 + tid;
+    // background group of this tile (uniform across the CTA)
+    const int g0 = tile_group(p, row0, cc);
+    if (g0 != cta_group) {
+      named_bar_sync(1, K1_ROWS);
+      sink_flush(p, sm, cta_group, tid, K1_ROWS);
+      named_bar_sync(1, K1_ROWS);
+      cta_group = g0;
+    }
+    mbar_wait(full + st, (uint32_t)((i / p.nstage) & 1));
+    uint32_t* rowp = reinterpret_cast<uint32_t*>(stages + (size_t)st * p.stage_bytes) + tid * RW;
+    const bool live = s < p.r1;
+    if (row0 + K1_ROWS > p.S && live) {
+      for (int w = 0; w < RW; ++w) rowp[w] = __ldg(p.G + s * RW + w);
+    }
+    if (live) {
+      uint32_t T1, M1, T2, M2;
+      if (ALIGNED) {
+        count_block_aligned(reinterpret_cast<const uint4*>(rowp), p.W1 >> 2, rot1, T1, M1);
+        count_block_aligned(reinterpret_cast<const uint4*>(rowp + p.W1), p.W2 >> 2, rot2, T2, M2);
+      } else {
+        count_block_words(rowp, p.W1, T1, M1);
+        count_block_words(rowp + p.W1, p.W2, T2, M2);
+      }
+      const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
+      const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
+      sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+    }
+    mbar_arrive(empty + st);
+  }
+  named_bar_sync(1, K1_ROWS);
+  sink_flush(p, sm, cta_group, tid, K1_ROWS);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 (counts entry)
+constexpr int K1C_THREADS = 256;
+__global__ void __launch_bounds__(K1C_THREADS) k1_counts(const __grid_constant__ KeyParams p) {
+  extern __shared__ __align__(16) uint8_t smem_c[];
+  SinkSmem sm;
+  sm.corner = reinterpret_cast<uint32_t*>(smem_c);
+  sm.h1a = sm.corner + p.cr * p.cc;
+  sm.h1b = sm.h1a + p.h1a;
+  const int nhist = p.cr * p.cc + p.h1a + p.h1b;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nhist; i += K1C_THREADS) sm.corner[i] = 0;
+  __syncthreads();
+  const long long ntiles = (p.r1 - p.r0 + K1C_THREADS - 1) / K1C_THREADS;
+  const long long t0 = ntiles * blockIdx.x / gridDim.x;
+  const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  ChromCache cc;
+  int cta_group = -2;
+  for (long long t = t0; t < t1; ++t) {
+    const long long row0 = p.r0 + t * K1C_THREADS;
+    const long long s = row0 + tid;
+    const int g0 = tile_group(p, row0, cc);
+    if (g0 != cta_group) {
+      __syncthreads();
+      sink_flush(p, sm, cta_group, tid, K1C_THREADS);
+      __syncthreads();
+      cta_group = g0;
+    }
+    if (s < p.r1) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.cnt) + s);  // (ref1 | alt1<<16, ref2 | alt2<<16)
+      sink_row(p, s, (int)(v.x & 0xFFFF), (int)(v.x >> 16), (int)(v.y & 0xFFFF), (int)(v.y >> 16), cta_group, sm, cc);
+    }
+  }
+  __syncthreads();
+  sink_flush(p, sm, cta_group, tid, K1C_THREADS);
+}
+
+// ------------------------------------------------------------------------------------------------ background finalize
+// ln b_k tables and interior totals B from the integer histograms (fold_1d_sfs :446-463 applied here).
+struct FinParams {
+  const uint32_t* hist;
+  long long gstride;
+  int NG, bins2d, R1, R2, n1, n2;
+  double* lb2;   // [NG][bins2d]
+  double* lb1a;  // [NG][n1+1]
+  double* lb1b;  // [NG][n2+1]
+  unsigned long long* Bsum;  // [NG][3] interior totals
+};
+
+__device__ __forceinline__ double ln_count(unsigned long long v) { return v ? log((double)v) : -INFINITY; }
+
+__global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__ FinParams p) {
+  const int g = blockIdx.y;
+  const uint32_t* h = p.hist + (long long)g * p.gstride;
+  unsigned long long local = 0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < p.bins2d; k += (long long)gridDim.x * blockDim.x) {
+    const uint32_t v = h[k];
+    p.lb2[(long long)g * p.bins2d + k] = ln_count(v);
+    if (k > 0 && k < p.bins2d - 1) local += v;
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.Bsum + g * 3, local);
+  if (blockIdx.x == 0) {
+    for (int pop = 0; pop < 2; ++pop) {
+      const int n = pop ? p.n2 : p.n1;
+      const uint32_t* raw = h + p.bins2d + (pop ? p.R1 : 0);
+      double* lb = pop ? p.lb1b + (long long)g * (p.n2 + 1) : p.lb1a + (long long)g * (p.n1 + 1);
+      unsigned long long loc = 0;
+      for (int k = threadIdx.x; k <= n; k += blockDim.x) {
+        unsigned long long v = raw[k];
+        if (2 * n - k != k) v += raw[2 * n - k];
+        lb[k] = ln_count(v);
+        if (k >= 1 && k <= n - 1) loc += v;
+      }
+      for (int o = 16; o; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+      if ((threadIdx.x & 31) == 0 && loc) atomicAdd(p.Bsum + g * 3 + 1 + pop, loc);
+    }
+  }
+}
+
+__global__ void k_u64_to_double(const unsigned long long* in, double* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+// precomputed (float) background: lb = ln b
+__global__ void k_log_table(const double* b, double* lb, long long n) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const double v = b[k];
+    lb[k] = v > 0.0 ? log(v) : (v == 0.0 ? -INFINITY : NAN);
+  }
+}
+
+__global__ void k_ln_int_table(double* t, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = i ? log((double)i) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 boundaries
+struct WinParams {
+  const int32_t* pos;
+  const long long* chrom_off;
+  const long long* cand_off;  // [C+1] candidate offsets per chromosome
+  int C;
+  long long W;                // window size in bp (fixed-bp) or SNPs (fixed-SNP)
+  long long ncand;
+  int32_t* wlo;
+  int32_t* whi;
+  int32_t* wchrom;
+  long long* wstart;
+  long long* wend;
+  int32_t* large;             // ids of windows with more than WCAP SNPs
+  int* nlarge;
+};
+
+__device__ __forceinline__ long long lower_bound_pos(const int32_t* pos, long long lo, long long hi, long long v) {
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if ((long long)__ldg(pos + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int cand_chrom(const WinParams& p, long long id) {
+  int lo = 0, hi = p.C;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(p.cand_off + mid) <= id) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// fixed-bp: window k of a chromosome holds positions [1+kW, (k+1)W]; position 0 falls in window 0 (:898, Q10)
+__global__ void __launch_bounds__(256) k2_bounds_bp(const __grid_constant__ WinParams p) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= p.ncand) return;
+  const int c = cand_chrom(p, id);
+  const long long k = id - __ldg(p.cand_off + c);
+  const long long clo = __ldg(p.chrom_off + c), chi = __ldg(p.chrom_off + c + 1);
+  const long long lo = k == 0 ? clo : lower_bound_pos(p.pos, clo, chi, 1 + k * p.W);
+  const long long hi = lower_bound_pos(p.pos, lo, chi, 1 + (k + 1) * p.W);
+  p.wlo[id] = (int32_t)lo;
+  p.whi[id] = (int32_t)hi;
+  p.wchrom[id] = c;
+  p.wstart[id] = 1 + k * p.W;
+  p.wend[id] = (k + 1) * p.W;
+  if (hi - lo > WCAP) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
+}
+
+// fixed-SNP: chunk j of a chromosome = rows [off + jN, off + (j+1)N); label per :1527/:1535
+__global__ void __launch_bounds__(256) k2_bounds_snp(const __grid_constant__ WinParams p) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= p.ncand) return;
+  const int c = cand_chrom(p, id);
+  const long long j = id - __ldg(p.cand_off + c);
+  const long long lo = __ldg(p.chrom_off + c) + j * p.W, hi = lo + p.W;
+  p.wlo[id] = (int32_t)lo;
+  p.whi[id] = (int32_t)hi;
+  p.wchrom[id] = c;
+  p.wstart[id] = j == 0 ? (long long)__ldg(p.pos + lo) : (long long)__ldg(p.pos + lo - 1) + 1;
+  p.wend[id] = (long long)__ldg(p.pos + hi - 1);
+  if (hi - lo > WCAP) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
+}
+
+// ------------------------------------------------------------------------------------------------ K3+K4 scoring
+struct ScoreParams {
+  const uint32_t* key;
+  const uint32_t* alts;
+  const uint8_t* flags;
+  const int32_t* wlo;
+  const int32_t* whi;
+  const int32_t* wchrom;
+  const int32_t* score_group;  // per chromosome (NULL = group 0)
+  long long ncand;
+  int n1, n2, bins2d, snp_mode;
+  const double* lb2;
+  const double* lb1a;
+  const double* lb1b;
+  const double* B;       // [NG][3]
+  const double* lnI;     // ln(m), m < LN_TABLE
+  // outputs
+  int32_t* r_count;
+  int32_t* r_n2;
+  int32_t* r_n1a;
+  int32_t* r_n1b;
+  double* r_T2;
+  double* r_T1a;
+  double* r_T1b;
+  uint8_t* r_flags;
+  // large-window path
+  const int32_t* large;
+  const int* nlarge;
+  uint32_t* scratch;     // [nCTA][bins2d + n1 + 1 + n2 + 1]
+};
+
+__device__ __forceinline__ double ln_mult(const ScoreParams& p, uint32_t m) {
+  return m < (uint32_t)LN_TABLE ? __ldg(p.lnI + m) : log((double)m);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// T = 2 * ( sum_s ln m_s  -  sum_s ln b_key(s)  -  N (ln N - ln B) )   ==  2 (ll_fg - ll_bg) of the reference
+__device__ __forceinline__ double clr_value(int N, double slm, double slb, double B, bool& none) {
+  none = (N == 0) || !(B != 0.0);
+  if (none) return NAN;
+  return 2.0 * (slm - slb - (double)N * (log((double)N) - log(B)));
+}
+
+__device__ __forceinline__ void write_result(const ScoreParams& p, long long id, int count, int nall, int N2, int N1a, int N1b,
+                                             double slm2, double slb2, double slm1a, double slb1a, double slm1b, double slb1b,
+                                             const double* Bg) {
+  bool none2, none1a, none1b;
+  const double T2 = clr_value(N2, slm2, slb2, Bg[0], none2);
+  const double T1a = clr_value(N1a, slm1a, slb1a, Bg[1], none1a);
+  const double T1b = clr_value(N1b, slm1b, slb1b, Bg[2], none1b);
+  uint8_t f = (none2 ? TDSFS_F_T2D_NONE : 0) | (none1a ? TDSFS_F_T1D_P1_NONE : 0) | (none1b ? TDSFS_F_T1D_P2_NONE : 0);
+  if (p.snp_mode && nall == 0) f |= TDSFS_F_SKIPPED;  // :1496 window skipped when its 2D spectrum sums to 0
+  p.r_count[id] = count;
+  p.r_n2[id] = N2;
+  p.r_n1a[id] = N1a;
+  p.r_n1b[id] = N1b;
+  p.r_T2[id] = T2;
+  p.r_T1a[id] = T1a;
+  p.r_T1b[id] = T1b;
+  p.r_flags[id] = f;
+}
+
+// 1D helper: folded bin of a raw alt count, 0 when the SNP does not enter the 1D likelihood
+// (alt == 0 skipped :430; folded bins 0 and n dropped :488)
+__device__ __forceinline__ int folded_interior(int a, int n) {
+  int f = min(a, 2 * n - a);
+  return (a != 0 && f >= 1 && f <= n - 1) ? f : 0;
+}
+
+// One warp per candidate window (<= WCAP SNPs).  Per-warp shared memory: open-addressing table of the window's
+// 2D bins (keys + counts), the slot of every SNP, and packed 16-bit 1D histograms.
+constexpr int SCORE_WARPS = 8;
+__host__ __device__ inline int score_warp_smem_words(int n1, int n2) {
+  return HASH_SLOTS * 2 + WCAP / 2 + (n1 + 2) / 2 + (n2 + 2) / 2;
+}
+
+__global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p, int warps_per_cta) {
+  extern __shared__ __align__(16) uint32_t sm32[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= warps_per_cta) return;
+  const int wwords = score_warp_smem_words(p.n1, p.n2);
+  uint32_t* tkey = sm32 + (size_t)warp * wwords;
+  uint32_t* tcnt = tkey + HASH_SLOTS;
+  uint16_t* slot = reinterpret_cast<uint16_t*>(tcnt + HASH_SLOTS);
+  uint32_t* h1a = tcnt + HASH_SLOTS + WCAP / 2;  // packed 16-bit bins
+  uint32_t* h1b = h1a + (p.n1 + 2) / 2;
+  for (int i = lane; i < HASH_SLOTS; i += 32) { tkey[i] = EMPTY_KEY; tcnt[i] = 0; }
+  for (int i = lane; i < (p.n1 + 2) / 2 + (p.n2 + 2) / 2; i += 32) h1a[i] = 0;
+  __syncwarp();
+
+  const long long nw = (long long)gridDim.x * warps_per_cta;
+  for (long long id = (long long)blockIdx.x * warps_per_cta + warp; id < p.ncand; id += nw) {
+    const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
+    const int cnt = hi - lo;
+    if (cnt == 0) {
+      if (lane == 0) { p.r_count[id] = 0; p.r_flags[id] = TDSFS_F_EMPTY; }
+      continue;
+    }
+    if (cnt > WCAP) continue;  // scored by k3_score_large
+    const int g = p.score_group ? __ldg(p.score_group + __ldg(p.wchrom + id)) : 0;
+    const double* lb2 = p.lb2 + (long long)g * p.bins2d;
+    const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
+    const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
+    const uint32_t last = (uint32_t)p.bins2d - 1;
+
+    int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
+    double slb2 = 0.0, slb1a = 0.0, slb1b = 0.0;
+    // phase 1: insert
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      if (i < cnt) {
+        const uint32_t k = __ldg(p.key + lo + i);
+        const uint32_t a = __ldg(p.alts + lo + i);
+        count += p.flags ? ((__ldg(p.flags + lo + i) >> 1) & 1) : 1;
+        nall += k != 0;
+        uint32_t sl = 0xFFFF;
+        if (k != 0 && k != last) {
+          uint32_t h = (k * 0x9E3779B1u) >> 22;  // 10 bits
+          while (true) {
+            const uint32_t prev = atomicCAS(tkey + h, EMPTY_KEY, k);
+            if (prev == EMPTY_KEY || prev == k) break;
+            h = (h + 1) & (HASH_SLOTS - 1);
+          }
+          atomicAdd(tcnt + h, 1u);
+          sl = h;
+          ++N2;
+          slb2 += __ldg(lb2 + k);
+        }
+        slot[i] = (uint16_t)sl;
+        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+        if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); ++N1a; slb1a += __ldg(lb1a + fa); }
+        if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); ++N1b; slb1b += __ldg(lb1b + fb); }
+      }
+    }
+    __syncwarp();
+    // phase 2: multiplicities  sum_s ln m_s == sum_k x_k ln x_k
+    double slm2 = 0.0, slm1a = 0.0, slm1b = 0.0;
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      if (i < cnt) {
+        const uint32_t sl = slot[i];
+        if (sl != 0xFFFF) slm2 += ln_mult(p, tcnt[sl]);
+        const uint32_t a = __ldg(p.alts + lo + i);
+        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+        if (fa) slm1a += ln_mult(p, (h1a[fa >> 1] >> (16 * (fa & 1))) & 0xFFFF);
+        if (fb) slm1b += ln_mult(p, (h1b[fb >> 1] >> (16 * (fb & 1))) & 0xFFFF);
+      }
+    }
+    __syncwarp();
+    // phase 3: clear only what was touched
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      if (i < cnt) {
+        const uint32_t sl = slot[i];
+        if (sl != 0xFFFF) { tkey[sl] = EMPTY_KEY; tcnt[sl] = 0; }
+        const uint32_t a = __ldg(p.alts + lo + i);
+        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+        if (fa) h1a[fa >> 1] = 0;
+        if (fb) h1b[fb >> 1] = 0;
+      }
+    }
+    __syncwarp();
+    N2 = warp_sum(N2); N1a = warp_sum(N1a); N1b = warp_sum(N1b); nall = warp_sum(nall); count = warp_sum(count);
+    slb2 = warp_sum(slb2); slb1a = warp_sum(slb1a); slb1b = warp_sum(slb1b);
+    slm2 = warp_sum(slm2); slm1a = warp_sum(slm1a); slm1b = warp_sum(slm1b);
+    if (lane == 0) write_result(p, id, count, nall, N2, N1a, N1b, slm2, slb2, slm1a, slb1a, slm1b, slb1b, p.B + g * 3);
+  }
+}
+
+// One CTA per large window; dense scratch histograms in global memory (L2 resident), cleared by re-walking the window.
+constexpr int LARGE_THREADS = 256;
+__global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_constant__ ScoreParams p) {
+  __shared__ double red_d[6][LARGE_THREADS / 32];
+  __shared__ int red_i[5][LARGE_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nl = *p.nlarge;
+  const long long sstride = (long long)p.bins2d + p.n1 + 1 + p.n2 + 1;
+  uint32_t* h2 = p.scratch + (long long)blockIdx.x * sstride;
+  uint32_t* h1a = h2 + p.bins2d;
+  uint32_t* h1b = h1a + p.n1 + 1;
+  const uint32_t last = (uint32_t)p.bins2d - 1;
+  for (int w = blockIdx.x; w < nl; w += gridDim.x) {
+    const long long id = p.large[w];
+    const int lo = p.wlo[id], hi = p.whi[id];
+    const int g = p.score_group ? p.score_group[p.wchrom[id]] : 0;
+    const double* lb2 = p.lb2 + (long long)g * p.bins2d;
+    const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
+    const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
+    int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
+    double slb2 = 0.0, slb1a = 0.0, slb1b = 0.0, slm2 = 0.0, slm1a = 0.0, slm1b = 0.0;
+    for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
+      const uint32_t k = p.key[s], a = p.alts[s];
+      count += p.flags ? ((p.flags[s] >> 1) & 1) : 1;
+      nall += k != 0;
+      if (k != 0 && k != last) { atomicAdd(h2 + k, 1u); ++N2; slb2 += lb2[k]; }
+      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      if (fa) { atomicAdd(h1a + fa, 1u); ++N1a; slb1a += lb1a[fa]; }
+      if (fb) { atomicAdd(h1b + fb, 1u); ++N1b; slb1b += lb1b[fb]; }
+    }
+    __syncthreads();
+    for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
+      const uint32_t k = p.key[s], a = p.alts[s];
+      if (k != 0 && k != last) slm2 += ln_mult(p, __ldcg(h2 + k));
+      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      if (fa) slm1a += ln_mult(p, __ldcg(h1a + fa));
+      if (fb) slm1b += ln_mult(p, __ldcg(h1b + fb));
+    }
+    __syncthreads();
+    for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
+      const uint32_t k = p.key[s], a = p.alts[s];
+      if (k != 0 && k != last) h2[k] = 0;
+      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      if (fa) h1a[fa] = 0;
+      if (fb) h1b[fb] = 0;
+    }
+    // block reduce
+    double dv[6] = {slb2, slb1a, slb1b, slm2, slm1a, slm1b};
+    int iv[5] = {N2, N1a, N1b, nall, count};
+    for (int q = 0; q < 6; ++q) { dv[q] = warp_sum(dv[q]); if (lane == 0) red_d[q][warp] = dv[q]; }
+    for (int q = 0; q < 5; ++q) { iv[q] = warp_sum(iv[q]); if (lane == 0) red_i[q][warp] = iv[q]; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 0; q < 6; ++q) { double t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_d[q][x]; dv[q] = t; }
+      for (int q = 0; q < 5; ++q) { int t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_i[q][x]; iv[q] = t; }
+      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[3], dv[0], dv[4], dv[1], dv[5], dv[2], p.B + g * 3);
+    }
+    __syncthreads();
+  }
+}
+
+// dense spectra of one window (calculate_2d_sfs / calculate_1d_sfs on window_data)
+__global__ void k_window_hist(const uint32_t* key, const uint32_t* alts, int lo, int hi, uint32_t* h2, uint32_t* h1a,
+                              uint32_t* h1b) {
+  for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
+    const uint32_t k = key[s], a = alts[s];
+    if (k) atomicAdd(h2 + k, 1u);
+    if (a & 0xFFFF) atomicAdd(h1a + (a & 0xFFFF), 1u);
+    if (a >> 16) atomicAdd(h1b + (a >> 16), 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ explicit likelihood
+// calculate_likelihood_1D/_2D on explicit interior vectors: T = 2 sum x (ln(x/N) - ln(b/B))
+__global__ void __launch_bounds__(256) k_likelihood(const long long* x, const double* b, long long n, double B, double* out,
+                                                    int* flag) {
+  __shared__ double sd[8];
+  __shared__ long long sn[8];
+  long long N = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) N += x[i];
+  for (int o = 16; o; o >>= 1) N += __shfl_xor_sync(0xffffffffu, N, o);
+  if ((threadIdx.x & 31) == 0) sn[threadIdx.x >> 5] = N;
+  __syncthreads();
+  N = 0;
+  for (int i = 0; i < 8; ++i) N += sn[i];
+  if (N == 0 || !(B != 0.0)) {
+    if (threadIdx.x == 0) { *out = NAN; *flag = 1; }
+    return;
+  }
+  const double lnN = log((double)N), lnB = log(B);
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long xi = x[i];
+    if (xi > 0) {
+      const double bi = b[i];
+      const double lb = bi > 0.0 ? log(bi) : (bi == 0.0 ? -INFINITY : NAN);
+      acc += (double)xi * ((log((double)xi) - lnN) - (lb - lnB));
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += sd[i];
+    *out = 2.0 * t;
+    *flag = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic panel
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
+
+// one thread per (row, word): 16 calls.  Ancestral frequency log-uniform on [1/(8n), 1-1/(8n)], per-population
+// drift ~ normal approximation of Balding-Nichols with F = fst, calls Binomial(2, p), iid missing.
+__global__ void __launch_bounds__(256) k_synth(uint32_t* G, long long S, long long snp0, int W1, int W2, int ns1, int ns2,
+                                               uint64_t seed, uint32_t miss_thr16, double fst) {
+  const int RW = W1 + W2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * RW) return;
+  const long long row = idx / RW;
+  const int w = (int)(idx - row * RW);
+  const int pop = w >= W1;
+  const int wi = pop ? w - W1 : w;
+  const int ns = pop ? ns2 : ns1;
+  const uint64_t snp = (uint64_t)(snp0 + row);
+  const uint64_t hs = mix64(seed ^ (snp * 0x9E3779B97F4A7C15ULL));
+  const double nn = 4.0 * (ns1 + ns2);  // 8 n with n = (ns1+ns2)/2
+  const double lo = 1.0 / nn, hi = 1.0 - 1.0 / nn;
+  const double pa = lo * exp(u01(hs) * log(hi / lo));
+  // drift: sum of 4 uniforms ~ N(0, 1/3) scaled to unit variance
+  const uint64_t hd = mix64(hs + 0x632BE59BD9B4E019ULL * (uint64_t)(pop + 1));
+  const double z = ((double)(hd & 0xFFFF) + (double)((hd >> 16) & 0xFFFF) + (double)((hd >> 32) & 0xFFFF) +
+                    (double)(hd >> 48)) * (1.0 / 65536.0) - 2.0;
+  double pp = pa + z * 1.7320508 * sqrt(fst * pa * (1.0 - pa));
+  pp = fmin(fmax(pp, 0.0), 1.0);
+  const uint32_t thr = (uint32_t)(pp * 4294967296.0 > 4294967295.0 ? 4294967295.0 : pp * 4294967296.0);
+  uint32_t word = 0;
+  for (int i = 0; i < 16; ++i) {
+    const int sample = wi * 16 + i;
+    if (sample >= ns) break;
+    const uint64_t h1 = mix64(hs ^ ((uint64_t)(pop * 1000003 + sample + 1) * 0xD6E8FEB86659FD93ULL));
+    const uint64_t h2 = mix64(h1);
+    const uint32_t a1 = (uint32_t)h1 < thr, a2 = (uint32_t)(h1 >> 32) < thr;
+    uint32_t code = (a1 + a2 == 0) ? 0u : (a1 + a2 == 1 ? 1u : 3u);
+    if ((uint32_t)(h2 & 0xFFFF) < miss_thr16) code = 2u;
+    word |= code << (2 * i);
+  }
+  G[idx] = word;
+}
+
+}  // namespace tdsfs
