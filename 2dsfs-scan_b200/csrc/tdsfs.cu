@@ -55,6 +55,9 @@ struct tdsfs_ctx {
   int C = 0;
   const uint32_t* dG = nullptr;
   bool own_G = false;
+  // pooled device buffers reused across loads (sizes in bytes)
+  void *pool_G = nullptr, *pool_cnt = nullptr, *pool_pos = nullptr, *pool_flags = nullptr;
+  size_t cap_G = 0, cap_cnt = 0, cap_pos = 0, cap_flags = 0;
   int W1 = 0, W2 = 0, ns1 = 0, ns2 = 0;
   const uint16_t* dCnt = nullptr;
   bool own_cnt = false;
@@ -69,8 +72,7 @@ struct tdsfs_ctx {
   long long* d_off = nullptr;
   std::vector<Chunk> chunks;
   // keys
-  uint32_t* d_key = nullptr;
-  uint32_t* d_alts = nullptr;
+  uint2* d_rec = nullptr;  // per-SNP (2D bin, raw alt pair)
   long long key_cap = 0;
   bool keys_ready = false;
   // background
@@ -84,10 +86,14 @@ struct tdsfs_ctx {
   double *d_lb2 = nullptr, *d_lb1a = nullptr, *d_lb1b = nullptr, *d_B = nullptr, *d_lnI = nullptr;
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
-  bool float_bg = false, tables_ready = false;
+  bool float_bg = false, tables_ready = false, fin_timed = false;
   int* d_err = nullptr;
   // windows / results
   long long ncand = 0, cand_cap = 0;
+  std::vector<long long> cand_off_host;  // cached candidate offsets of (cand_W, cand_snp)
+  long long cand_W = -1;
+  int cand_snp = -1;
+  int groups_mode = -1, groups_chrom = -1;  // what d_bg_group / d_score_group currently hold
   long long* d_cand_off = nullptr;
   int32_t *d_wlo = nullptr, *d_whi = nullptr, *d_wchrom = nullptr, *d_large = nullptr;
   long long *d_wstart = nullptr, *d_wend = nullptr;
@@ -162,11 +168,19 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   return 0;
 }
 
+static int pool_get(void** pool, size_t* cap, size_t bytes, void** out) {
+  if (bytes > *cap) {
+    if (*pool) cudaFree(*pool);
+    *pool = nullptr;
+    *cap = 0;
+    CK(cudaMalloc(pool, std::max<size_t>(bytes, 256)));
+    *cap = std::max<size_t>(bytes, 256);
+  }
+  *out = *pool;
+  return 0;
+}
+
 static void free_data(tdsfs_ctx* c) {
-  if (c->own_G) { void* p = (void*)c->dG; cudaFree(p); }
-  if (c->own_cnt) { void* p = (void*)c->dCnt; cudaFree(p); }
-  if (c->own_pos) { void* p = (void*)c->dPos; cudaFree(p); }
-  if (c->own_flags) { void* p = (void*)c->dFlags; cudaFree(p); }
   c->dG = nullptr; c->dCnt = nullptr; c->dPos = nullptr; c->dFlags = nullptr;
   c->own_G = c->own_cnt = c->own_pos = c->own_flags = false;
   dev_free(c->dFix);
@@ -175,6 +189,8 @@ static void free_data(tdsfs_ctx* c) {
   for (auto& ch : c->chunks) if (ch.ev) cudaEventDestroy(ch.ev);
   c->chunks.clear();
   c->keys_ready = c->tables_ready = c->results_ready = false;
+  c->cand_W = -1;
+  c->groups_mode = -1;
 }
 
 extern "C" void tdsfs_destroy(tdsfs_t* c) {
@@ -182,7 +198,11 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_data(c);
-  dev_free(c->d_key); dev_free(c->d_alts); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
+  if (c->pool_G) cudaFree(c->pool_G);
+  if (c->pool_cnt) cudaFree(c->pool_cnt);
+  if (c->pool_pos) cudaFree(c->pool_pos);
+  if (c->pool_flags) cudaFree(c->pool_flags);
+  dev_free(c->d_rec); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
   dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
   dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
   dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend); dev_free(c->d_nlarge);
@@ -221,16 +241,16 @@ extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold)
 
 // ------------------------------------------------------------------------------------------------ data
 template <typename T>
-static int adopt_or_upload(tdsfs_ctx* c, const T* src, long long n, const T** dst, bool* own, long long pad_elems = 0) {
+static int adopt_or_upload(tdsfs_ctx* c, const T* src, long long n, const T** dst, bool* own, void** pool, size_t* cap) {
   if (is_device_ptr(src)) {
     *dst = src;
     *own = false;
     return 0;
   }
-  T* d = nullptr;
-  CKR(dev_alloc(&d, n + pad_elems));
+  void* d = nullptr;
+  CKR(pool_get(pool, cap, (size_t)n * sizeof(T), &d));
   CK(cudaMemcpyAsync(d, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  *dst = d;
+  *dst = (const T*)d;
   *own = true;
   return 0;
 }
@@ -247,16 +267,16 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
   c->h_off.assign(chrom_off, chrom_off + C + 1);
   CKR(dev_alloc(&c->d_off, C + 1));
   CK(cudaMemcpyAsync(c->d_off, chrom_off, (size_t)(C + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-  CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos));
+  CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos, &c->pool_pos, &c->cap_pos));
   if (flags) {
     if (need_flag_copy && is_device_ptr(flags)) {
-      uint8_t* d = nullptr;
-      CKR(dev_alloc(&d, S));
+      void* d = nullptr;
+      CKR(pool_get(&c->pool_flags, &c->cap_flags, (size_t)S, &d));
       CK(cudaMemcpyAsync(d, flags, (size_t)S, cudaMemcpyDeviceToDevice, c->stream));
-      c->dFlags = d;
+      c->dFlags = (const uint8_t*)d;
       c->own_flags = true;
     } else {
-      CKR(adopt_or_upload(c, flags, S, &c->dFlags, &c->own_flags));
+      CKR(adopt_or_upload(c, flags, S, &c->dFlags, &c->own_flags, &c->pool_flags, &c->cap_flags));
     }
   }
   // last position of every chromosome (sizes the fixed-bp candidate list)
@@ -274,10 +294,8 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
       }
   }
   if (S > c->key_cap) {
-    dev_free(c->d_key);
-    dev_free(c->d_alts);
-    CKR(dev_alloc(&c->d_key, S));
-    CKR(dev_alloc(&c->d_alts, S));
+    dev_free(c->d_rec);
+    CKR(dev_alloc(&c->d_rec, S));
     c->key_cap = S;
   }
   return 0;
@@ -290,7 +308,7 @@ extern "C" int tdsfs_load_counts(tdsfs_t* c, const uint16_t* cnt, int64_t S, con
   CK(cudaSetDevice(c->device));
   free_data(c);
   CKR(load_common(c, S, pos, (const long long*)chrom_off, C, snp_flags, false));
-  CKR(adopt_or_upload(c, cnt, S * 4, &c->dCnt, &c->own_cnt));
+  CKR(adopt_or_upload(c, cnt, S * 4, &c->dCnt, &c->own_cnt, &c->pool_cnt, &c->cap_cnt));
   if (((uintptr_t)c->dCnt & 7) != 0) return fail(TDSFS_ERR_ARG, "cnt must be 8-byte aligned");
   return finish(c);
 }
@@ -302,7 +320,7 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
   if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
   if (words1 < 1 || words2 < 1 || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
     return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d)", words1, words2, ns1, ns2);
-  if ((long long)(words1 + words2) * 512 > 64 * 1024) return fail(TDSFS_ERR_ARG, "row too wide: more than 2048 samples per 128-row tile stage is not supported yet");
+  if ((long long)(words1 + words2) * BLK * 4 > 32 * 1024) return fail(TDSFS_ERR_ARG, "row too wide: more than 4096 samples per SNP is not supported yet");
   CK(cudaSetDevice(c->device));
   free_data(c);
   const bool has_fix = fixups && n_fixups > 0;
@@ -325,9 +343,9 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
       hflags[(size_t)f.snp] |= 4;
     }
     if (!c->own_flags) {
-      uint8_t* d = nullptr;
-      CKR(dev_alloc(&d, S));
-      c->dFlags = d;
+      void* d = nullptr;
+      CKR(pool_get(&c->pool_flags, &c->cap_flags, (size_t)S, &d));
+      c->dFlags = (const uint8_t*)d;
       c->own_flags = true;
     }
     CK(cudaMemcpyAsync((void*)c->dFlags, hflags.data(), (size_t)S, cudaMemcpyHostToDevice, c->stream));
@@ -343,19 +361,20 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
     c->chunks.push_back({0, S, nullptr});
   } else {
     // chunked asynchronous upload on the copy stream; tdsfs_background's count kernel consumes chunk by chunk
-    uint32_t* d = nullptr;
-    const long long padded_rows = (S + K1_ROWS - 1) / K1_ROWS * K1_ROWS;
-    CKR(dev_alloc(&d, padded_rows * RW));
+    void* dv = nullptr;
+    const long long nblk = (S + BLK - 1) / BLK;
+    const long long blk_bytes = RW * BLK * 4;
+    CKR(pool_get(&c->pool_G, &c->cap_G, (size_t)(nblk * blk_bytes), &dv));
+    uint32_t* d = (uint32_t*)dv;
     c->dG = d;
     c->own_G = true;
-    const long long row_bytes = RW * 4;
-    long long rows_per_chunk = std::max<long long>(K1_ROWS, (64LL << 20) / row_bytes / K1_ROWS * K1_ROWS);
+    const long long blks_per_chunk = std::max<long long>(K1_ROWS / BLK, (64LL << 20) / blk_bytes / (K1_ROWS / BLK) * (K1_ROWS / BLK));
     CK(cudaStreamSynchronize(c->stream));
-    for (long long r0 = 0; r0 < S; r0 += rows_per_chunk) {
-      const long long r1 = std::min<long long>(S, r0 + rows_per_chunk);
-      Chunk ch{r0, r1, nullptr};
+    for (long long bb0 = 0; bb0 < nblk; bb0 += blks_per_chunk) {
+      const long long bb1 = std::min<long long>(nblk, bb0 + blks_per_chunk);
+      Chunk ch{bb0 * BLK, std::min<long long>(S, bb1 * BLK), nullptr};
       CK(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
-      CK(cudaMemcpyAsync(d + r0 * RW, (const uint8_t*)G + r0 * row_bytes, (size_t)((r1 - r0) * row_bytes),
+      CK(cudaMemcpyAsync((uint8_t*)d + bb0 * blk_bytes, (const uint8_t*)G + bb0 * blk_bytes, (size_t)((bb1 - bb0) * blk_bytes),
                          cudaMemcpyHostToDevice, c->copy_stream));
       CK(cudaEventRecord(ch.ev, c->copy_stream));
       c->chunks.push_back(ch);
@@ -384,7 +403,7 @@ static void fill_key_params(tdsfs_ctx* c, KeyParams& p) {
   p.ns1 = c->ns1; p.ns2 = c->ns2; p.W1 = c->W1; p.W2 = c->W2;
   p.S = c->S;
   p.G = c->dG; p.cnt = c->dCnt; p.pos = c->dPos; p.flags = c->dFlags; p.fix = c->dFix; p.nfix = c->nfix;
-  p.key = c->d_key; p.alts = c->d_alts; p.hist = c->d_hist; p.gstride = c->gstride;
+  p.rec = c->d_rec; p.hist = c->d_hist; p.gstride = c->gstride;
   p.chrom_off = c->d_off; p.C = c->C; p.err = c->d_err;
   p.cr = std::min(c->R1, CORNER); p.cc = std::min(c->R2, CORNER);
   p.h1a = std::min(c->R1, H1CAP); p.h1b = std::min(c->R2, H1CAP);
@@ -422,43 +441,46 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   p.bg_group = nullptr;
   p.uniform_group = mode == TDSFS_BG_GENOME ? 0 : -1;
   if (mode == TDSFS_BG_PER_CHROM || mode == TDSFS_BG_CHROM) {
-    std::vector<int32_t> g(c->C);
-    for (int i = 0; i < c->C; ++i) g[i] = mode == TDSFS_BG_PER_CHROM ? i : (i == bg_chrom ? 0 : -1);
-    dev_free(c->d_bg_group);
-    CKR(dev_alloc(&c->d_bg_group, c->C));
-    CK(cudaMemcpyAsync(c->d_bg_group, g.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // g is a stack-lifetime buffer
+    if (c->groups_mode != mode || c->groups_chrom != bg_chrom) {  // upload once per (mode, chromosome)
+      std::vector<int32_t> g(c->C), sg(c->C);
+      for (int i = 0; i < c->C; ++i) {
+        g[i] = mode == TDSFS_BG_PER_CHROM ? i : (i == bg_chrom ? 0 : -1);
+        sg[i] = i;
+      }
+      dev_free(c->d_bg_group);
+      dev_free(c->d_score_group);
+      CKR(dev_alloc(&c->d_bg_group, c->C));
+      CKR(dev_alloc(&c->d_score_group, c->C));
+      CK(cudaMemcpyAsync(c->d_bg_group, g.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(c->d_score_group, sg.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));  // g / sg are stack-lifetime buffers
+      c->groups_mode = mode;
+      c->groups_chrom = bg_chrom;
+    }
     p.bg_group = c->d_bg_group;
-  }
-  if (mode == TDSFS_BG_PER_CHROM) {
-    std::vector<int32_t> g(c->C);
-    for (int i = 0; i < c->C; ++i) g[i] = i;
-    dev_free(c->d_score_group);
-    CKR(dev_alloc(&c->d_score_group, c->C));
-    CK(cudaMemcpyAsync(c->d_score_group, g.data(), (size_t)c->C * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
   }
 
   const int hist_bytes = (p.cr * p.cc + p.h1a + p.h1b) * 4;
   if (c->dG) {
     const int RW = c->W1 + c->W2;
-    p.stage_bytes = K1_ROWS * RW * 4;
-    int nstage = std::max(2, std::min(8, (96 * 1024) / p.stage_bytes));
-    p.nstage = nstage;
-    const int smem = nstage * p.stage_bytes + nstage * 16 + hist_bytes;
-    const bool aligned = (c->W1 % 4 == 0) && (c->W2 % 4 == 0);
-    auto kern = aligned ? k1_genotypes<true> : k1_genotypes<false>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
-    occ = std::max(1, occ);
+    const int blk_bytes = RW * BLK * 4;
+    p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile: >= one 32-SNP block, ~4-8 KB
+    p.stage_bytes = p.tile_blocks * blk_bytes;
+    // ring = k stages per consumer warp (k >= 2 when they fit): one being counted, the others in flight from HBM
+    const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 16);
+    if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
+    p.cwarps = std::min(K1_CWARPS, fit);
+    p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));
+    const int smem = p.nstage * p.stage_bytes + p.nstage * 16 + hist_bytes;
+    CK(cudaFuncSetAttribute(k1_genotypes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     for (auto& ch : c->chunks) {
       if (ch.r1 <= ch.r0) continue;
       if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
       p.r0 = ch.r0; p.r1 = ch.r1;
-      const long long ntiles = (ch.r1 - ch.r0 + K1_ROWS - 1) / K1_ROWS;
-      const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count * occ);
-      kern<<<grid, K1_THREADS, smem, st>>>(p);
+      const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
+      const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
+      const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
+      k1_genotypes<<<grid, K1_THREADS, smem, st>>>(p);
       c->launches++;
     }
   } else {
@@ -482,8 +504,6 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       c->keys_ready = false;
       return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
     }
-    cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
-    c->ms[5] = c->ms[0];
   }
   return 0;
 }
@@ -559,8 +579,8 @@ extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[EV_FIN1], st));
   c->tables_ready = true;
+  c->fin_timed = true;
   CKR(finish(c));
-  if (c->sync) cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
   return 0;
 }
 
@@ -639,15 +659,17 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
   if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  std::vector<long long> off;
-  CKR(candidates(c, W, snp_mode, off));
-  const long long ncand = off[c->C];
+  if (c->cand_W != W || c->cand_snp != (int)snp_mode) {  // window plan cached per (size, mode): no sync in steady state
+    CKR(candidates(c, W, snp_mode, c->cand_off_host));
+    CKR(ensure_windows(c, c->cand_off_host[c->C]));
+    dev_free(c->d_cand_off);
+    CKR(dev_alloc(&c->d_cand_off, c->C + 1));
+    CK(cudaMemcpyAsync(c->d_cand_off, c->cand_off_host.data(), (size_t)(c->C + 1) * 8, cudaMemcpyHostToDevice, st));
+    c->cand_W = W;
+    c->cand_snp = snp_mode;
+  }
+  const long long ncand = c->cand_off_host[c->C];
   if (out && cap < ncand) return fail(TDSFS_ERR_ARG, "result capacity %lld < %lld candidate windows", (long long)cap, ncand);
-  CKR(ensure_windows(c, ncand));
-  dev_free(c->d_cand_off);
-  CKR(dev_alloc(&c->d_cand_off, c->C + 1));
-  CK(cudaMemcpyAsync(c->d_cand_off, off.data(), (size_t)(c->C + 1) * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // `off` is a local buffer
   CK(cudaEventRecord(c->ev[EV_SC0], st));
   c->ncand = ncand;
   if (ncand > 0) {
@@ -663,13 +685,14 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
 
     ScoreParams s;
     memset(&s, 0, sizeof s);
-    s.key = c->d_key; s.alts = c->d_alts; s.flags = c->dFlags; s.wlo = c->d_wlo; s.whi = c->d_whi; s.wchrom = c->d_wchrom;
+    s.rec = c->d_rec; s.flags = c->dFlags; s.wlo = c->d_wlo; s.whi = c->d_whi; s.wchrom = c->d_wchrom;
     s.score_group = c->per_chrom_scoring ? c->d_score_group : nullptr;
     s.ncand = ncand; s.n1 = c->n1; s.n2 = c->n2; s.bins2d = c->bins2d; s.snp_mode = snp_mode;
     s.lb2 = c->d_lb2; s.lb1a = c->d_lb1a; s.lb1b = c->d_lb1b; s.B = c->d_B; s.lnI = c->d_lnI;
     s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
     // small windows: one warp each
+    if (!score_small_ok(c->n1, c->n2, c->bins2d)) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer (n <= 1023 per population)");
     const int wwords = score_warp_smem_words(c->n1, c->n2);
     int warps = std::min(SCORE_WARPS, (200 * 1024) / (wwords * 4));
     if (warps < 1) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer");
@@ -707,40 +730,34 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     if (n_windows) *n_windows = ncand;
     CKR(finish(c));
   }
-  if (c->sync || out) {
-    cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
-    cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
-    cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
-    cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);
-  }
   return 0;
 }
 
 extern "C" int tdsfs_scan_bp(tdsfs_t* c, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, W, false, out, cap, n); }
 extern "C" int tdsfs_scan_snp(tdsfs_t* c, int64_t N, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, N, true, out, cap, n); }
 
+// Synchronise and surface deferred device-side errors (range check of the count kernel).
+extern "C" int tdsfs_check(tdsfs_t* c) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  int err = 0;
+  CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
+  if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
+  return 0;
+}
+
 extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) {
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
   const bool was_sync = c->sync;
-  c->sync = false;  // one synchronisation at the end of the whole pass
+  c->sync = false;  // at most one synchronisation, at the end of the whole pass
   int r = tdsfs_background(c, bg_mode, 0, -1, -1);
   if (!r) r = tdsfs_finalize_background(c);
   if (!r) r = scan(c, W, false, out, cap, n);
   c->sync = was_sync;
   if (r) return r;
-  CK(cudaStreamSynchronize(c->stream));
-  int err = 0;
-  CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
-  if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
-  cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
-  cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
-  cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
-  cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
-  cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
-  cudaEventElapsedTime(&c->ms[5], c->ev[EV_BG0], c->ev[EV_K1]);
-  cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);
-  cudaEventElapsedTime(&c->ms[7], c->ev[EV_BG0], c->ev[EV_K3L]);
-  return 0;
+  if (!was_sync && !out) return 0;  // fully asynchronous: the caller synchronises and may call tdsfs_check
+  return tdsfs_check(c);
 }
 
 extern "C" int tdsfs_window_spectra(tdsfs_t* c, int64_t window, uint64_t* s2, uint64_t* s1a, uint64_t* s1b) {
@@ -757,7 +774,7 @@ extern "C" int tdsfs_window_spectra(tdsfs_t* c, int64_t window, uint64_t* s2, ui
   CKR(dev_alloc(&d, words));
   CK(cudaMemsetAsync(d, 0, (size_t)words * 4, st));
   if (hi > lo) {
-    k_window_hist<<<std::min(1024, (hi - lo + 255) / 256), 256, 0, st>>>(c->d_key, c->d_alts, lo, hi, d, d + c->bins2d, d + c->bins2d + c->R1);
+    k_window_hist<<<std::min(1024, (hi - lo + 255) / 256), 256, 0, st>>>(c->d_rec, lo, hi, d, d + c->bins2d, d + c->bins2d + c->R1);
     c->launches++;
   }
   std::vector<uint32_t> h((size_t)words);
@@ -816,6 +833,20 @@ extern "C" int tdsfs_synth_genotypes(tdsfs_t* c, void* G_dev, int64_t S, int64_t
 
 extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
   if (!c || !ms) return fail(TDSFS_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 8; ++i) c->ms[i] = 0.f;
+  if (c->keys_ready) cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
+  if (c->fin_timed) cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
+  if (c->results_ready) {
+    cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
+    cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
+    cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
+    cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);
+    if (c->keys_ready) cudaEventElapsedTime(&c->ms[7], c->ev[EV_BG0], c->ev[EV_K3L]);
+  }
+  c->ms[5] = c->ms[0];
+  cudaGetLastError();
   for (int i = 0; i < n && i < 8; ++i) ms[i] = c->ms[i];
   return 0;
 }

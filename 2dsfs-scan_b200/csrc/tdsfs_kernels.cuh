@@ -18,8 +18,11 @@
 namespace tdsfs {
 
 // ------------------------------------------------------------------------------------------------ constants
-constexpr int K1_ROWS = 128;          // rows per TMA tile == consumer threads of the genotype count kernel
-constexpr int K1_THREADS = K1_ROWS + 32;  // + one producer warp
+constexpr int BLK = 32;               // SNPs per block of the block-transposed genotype layout ("B32")
+constexpr int K1_CWARPS = 12;         // consumer warps of the genotype count kernel (one 32-SNP block at a time each)
+constexpr int K1_CONS = K1_CWARPS * 32;
+constexpr int K1_THREADS = K1_CONS + 32;  // + one TMA producer warp
+constexpr int K1_ROWS = 128;          // row granularity of host-side upload chunks (multiple of BLK)
 constexpr int CORNER = 64;            // privatised low-count corner of the 2D background histogram (per CTA, smem)
 constexpr int H1CAP = 2048;           // privatised 1D bins per population (per CTA, smem)
 constexpr int HASH_SLOTS = 1024;      // per-warp open-addressing table of the window scorer
@@ -37,8 +40,8 @@ struct KeyParams {
   const uint8_t* flags;
   const tdsfs_fixup_t* fix;
   long long nfix;
-  uint32_t* key;      // folded 2D bin index a1'*(2n2+1)+a2'; 0 = contributes nothing
-  uint32_t* alts;     // raw alt1 | raw alt2 << 16 (0 when filtered out)
+  uint2* rec;         // per SNP: x = folded 2D bin index a1'*(2n2+1)+a2' (0 = contributes nothing),
+                      //          y = raw alt1 | raw alt2 << 16 (0 when filtered out)
   uint32_t* hist;     // [group][bins2d | R1 | R2]
   long long gstride;
   const int32_t* bg_group;  // per chromosome -> background group, -1 = not in any background; NULL = uniform_group
@@ -49,7 +52,9 @@ struct KeyParams {
   int* err;                 // bit0: count out of range
   int cr, cc;               // corner dims actually used: min(R1, CORNER), min(R2, CORNER)
   int h1a, h1b;             // privatised 1D bins: min(R1, H1CAP), min(R2, H1CAP)
-  int nstage, stage_bytes;
+  int nstage, stage_bytes;  // K1 ring: stages of `tile_blocks` 32-SNP blocks; nstage is a multiple of cwarps
+  int tile_blocks;
+  int cwarps;               // active consumer warps (<= K1_CWARPS)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -157,41 +162,28 @@ struct PopCounts {
   }
 };
 
-// words of one population block, 16-byte aligned in smem, nchunk = W/4 chunks, bank-rotated start `rot`
-__device__ __forceinline__ void count_block_aligned(const uint4* blk, int nchunk, int rot, uint32_t& T, uint32_t& M) {
+// One population block of one SNP in the B32 layout: word w of the lane's SNP sits at blk[w * 32] (conflict-free LDS.32,
+// immediate offsets after unrolling).  Returns T = popcount of all bits, M = number of missing calls.
+__device__ __forceinline__ void count_block_b32(const uint32_t* blk, int W, uint32_t& T, uint32_t& M) {
   PopCounts pc;
-  int c = rot;  // rot < nchunk guaranteed by the caller
-  int i = 0;
-  for (; i + 2 <= nchunk; i += 2) {
-    uint4 a = blk[c];
-    c = (c + 1 == nchunk) ? 0 : c + 1;
-    uint4 b = blk[c];
-    c = (c + 1 == nchunk) ? 0 : c + 1;
+  int w = 0;
+  for (; w + 8 <= W; w += 8) {
+    const uint32_t* q = blk + w * BLK;
+    uint4 a = make_uint4(q[0], q[BLK], q[2 * BLK], q[3 * BLK]);
+    uint4 b = make_uint4(q[4 * BLK], q[5 * BLK], q[6 * BLK], q[7 * BLK]);
     pc.chunk8(a, b);
   }
-  if (i < nchunk) {
-    uint4 a = blk[c];
-    pc.chunk4(a.x, a.y, a.z, a.w);
+  if (w + 4 <= W) {
+    const uint32_t* q = blk + w * BLK;
+    pc.chunk4(q[0], q[BLK], q[2 * BLK], q[3 * BLK]);
+    w += 4;
   }
-  T = pc.bits.total();
-  M = pc.miss.total();
-}
-
-// generic: W words, 4-byte aligned
-__device__ __forceinline__ void count_block_words(const uint32_t* blk, int W, uint32_t& T, uint32_t& M) {
-  PopCounts pc;
-  int i = 0;
-  for (; i + 8 <= W; i += 8) {
-    uint4 a = make_uint4(blk[i], blk[i + 1], blk[i + 2], blk[i + 3]);
-    uint4 b = make_uint4(blk[i + 4], blk[i + 5], blk[i + 6], blk[i + 7]);
-    pc.chunk8(a, b);
-  }
-  for (; i < W; i += 4) {
-    uint32_t w0 = blk[i];
-    uint32_t w1 = (i + 1 < W) ? blk[i + 1] : 0u;
-    uint32_t w2 = (i + 2 < W) ? blk[i + 2] : 0u;
-    uint32_t w3 = (i + 3 < W) ? blk[i + 3] : 0u;
-    pc.chunk4(w0, w1, w2, w3);
+  if (w < W) {
+    const uint32_t* q = blk + w * BLK;
+    const uint32_t w0 = q[0];
+    const uint32_t w1 = (w + 1 < W) ? q[BLK] : 0u;
+    const uint32_t w2 = (w + 2 < W) ? q[2 * BLK] : 0u;
+    pc.chunk4(w0, w1, w2, 0u);
   }
   T = pc.bits.total();
   M = pc.miss.total();
@@ -280,8 +272,7 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
       }
     }
   }
-  p.key[s] = key;
-  p.alts[s] = alts;
+  p.rec[s] = make_uint2(key, alts);
 }
 
 // flush the CTA-private histograms of group g into global memory (threads tid..nthr of the sink group)
@@ -311,13 +302,13 @@ __device__ __forceinline__ int tile_group(const KeyParams& p, long long row0, Ch
 }
 
 // ------------------------------------------------------------------------------------------------ K1 (genotypes)
-// Persistent CTAs; warp 4 = TMA producer streaming 128-row tiles of the genotype matrix into a shared-memory ring
-// (cp.async.bulk + mbarrier), warps 0-3 = consumers, one SNP row per thread: bit-sliced popcount of the row's
-// two population blocks, fold/key, coalesced key stores, privatised background histograms.
-template <bool ALIGNED>
-__global__ void __launch_bounds__(K1_THREADS) k1_genotypes(const __grid_constant__ KeyParams p) {
+// One persistent CTA per SM.  Warp 16 = TMA producer: streams tiles of `tile_blocks` 32-SNP blocks (contiguous in the B32
+// layout) into a deep shared-memory ring with cp.async.bulk + mbarrier.  Warps 0-15 = consumers: tile i of the CTA goes to
+// warp i % 16; each lane owns one SNP of the block: bit-sliced popcount of its two population blocks straight from
+// shared memory (word w at +128 B: bank = lane), fold/key, one coalesced 8-byte record store, privatised histograms.
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_constant__ KeyParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int RW = p.W1 + p.W2;
   uint8_t* stages = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
@@ -331,33 +322,39 @@ __global__ void __launch_bounds__(K1_THREADS) k1_genotypes(const __grid_constant
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) {
       mbar_init(full + i, 1);
-      mbar_init(empty + i, K1_ROWS);
+      mbar_init(empty + i, 1);
     }
     fence_barrier_init();
   }
   for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
   __syncthreads();
 
-  // contiguous tile range of this CTA
-  const long long ntiles = (p.r1 - p.r0 + K1_ROWS - 1) / K1_ROWS;
+  // contiguous range of tiles of this CTA; a tile = tile_blocks blocks of 32 SNPs
+  const long long b0 = p.r0 / BLK, b1 = (p.r1 + BLK - 1) / BLK;  // r0 is a multiple of BLK
+  const long long ntiles = (b1 - b0 + p.tile_blocks - 1) / p.tile_blocks;
   const long long t0 = ntiles * blockIdx.x / gridDim.x;
   const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-  const uint32_t tile_bytes = (uint32_t)p.stage_bytes;
+  const long long block_words = (long long)RW * BLK;
 
-  if (tid >= K1_ROWS) {
-    // ---------------- producer warp ----------------
-    if (tid == K1_ROWS) {
-      long long i = 0;
-      for (long long t = t0; t < t1; ++t, ++i) {
-        const int st = (int)(i % p.nstage);
-        if (i >= p.nstage) mbar_wait(empty + st, (uint32_t)(((i / p.nstage) - 1) & 1));
-        const long long row0 = p.r0 + t * K1_ROWS;
-        if (row0 + K1_ROWS <= p.S) {
-          mbar_arrive_expect_tx(full + st, tile_bytes);
-          bulk_g2s(stages + (size_t)st * p.stage_bytes, p.G + row0 * RW, tile_bytes, full + st);
-        } else {
-          mbar_arrive(full + st);  // ragged last tile: consumers fetch their own rows
+  if (warp == K1_CWARPS) {
+    // ---------------- producer: one lane, one bulk copy per tile, ring position kept incrementally ----------------
+    if (lane == 0) {
+      const uint32_t full_bytes = (uint32_t)(p.tile_blocks * block_words * 4);
+      const uint32_t* src = p.G + (b0 + t0 * p.tile_blocks) * block_words;
+      const long long n = t1 - t0;
+      int st = 0;
+      uint32_t ph = 1;  // parity of the previous use of the stage (first pass: nothing to wait for)
+      for (long long i = 0; i < n; ++i) {
+        if (i >= p.nstage) mbar_wait(empty + st, ph);
+        uint32_t bytes = full_bytes;
+        if (i == n - 1) {  // the very last tile of the launch may be short
+          const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+          bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
         }
+        mbar_arrive_expect_tx(full + st, bytes);
+        bulk_g2s(stages + (size_t)st * p.stage_bytes, src, bytes, full + st);
+        src += (size_t)p.tile_blocks * block_words;
+        if (++st == p.nstage) { st = 0; ph ^= 1; }
       }
     }
     return;
@@ -365,53 +362,35 @@ __global__ void __launch_bounds__(K1_THREADS) k1_genotypes(const __grid_constant
 
   // ---------------- consumers ----------------
   ChromCache cc;
-  int cta_group = -2;
-  // bank rotation for conflict-free 16-byte shared loads (DESIGN.md "K1 shared-memory access")
-  int rot1 = 0, rot2 = 0;
-  if (ALIGNED) {
-    const int rc = RW >> 2;  // 16-byte chunks per row
-    int k = 0;
-    while (k < 3 && ((rc >> k) & 1) == 0) ++k;
-    const int rot = (tid & 7) >> (3 - k);
-    rot1 = rot % (p.W1 >> 2);
-    rot2 = rot % (p.W2 >> 2);
-  }
-  long long i = 0;
-  for (long long t = t0; t < t1; ++t, ++i) {
-    const int st = (int)(i % p.nstage);
-    const long long row0 = p.r0 + t * K1_ROWS;
-    const long long s = row0 + tid;
-    // background group of this tile (uniform across the CTA)
-    const int g0 = tile_group(p, row0, cc);
-    if (g0 != cta_group) {
-      named_bar_sync(1, K1_ROWS);
-      sink_flush(p, sm, cta_group, tid, K1_ROWS);
-      named_bar_sync(1, K1_ROWS);
-      cta_group = g0;
-    }
-    mbar_wait(full + st, (uint32_t)((i / p.nstage) & 1));
-    uint32_t* rowp = reinterpret_cast<uint32_t*>(stages + (size_t)st * p.stage_bytes) + tid * RW;
-    const bool live = s < p.r1;
-    if (row0 + K1_ROWS > p.S && live) {
-      for (int w = 0; w < RW; ++w) rowp[w] = __ldg(p.G + s * RW + w);
-    }
-    if (live) {
-      uint32_t T1, M1, T2, M2;
-      if (ALIGNED) {
-        count_block_aligned(reinterpret_cast<const uint4*>(rowp), p.W1 >> 2, rot1, T1, M1);
-        count_block_aligned(reinterpret_cast<const uint4*>(rowp + p.W1), p.W2 >> 2, rot2, T2, M2);
-      } else {
-        count_block_words(rowp, p.W1, T1, M1);
-        count_block_words(rowp + p.W1, p.W2, T2, M2);
+  const int cta_group = (t1 > t0) ? tile_group(p, p.r0 + t0 * p.tile_blocks * BLK, cc) : -1;
+  // Stage st is always consumed by warp st % cwarps (nstage is a multiple of cwarps), so the warp that waits for use
+  // u+1 of a stage is the one that released use u: a parity wait can never alias a phase two uses away.
+  int st = warp;
+  uint32_t ph = 0;
+  for (long long i = warp; warp < p.cwarps && t0 + i < t1; i += p.cwarps) {
+    const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+    const int nb = (int)min((long long)p.tile_blocks, b1 - blk0);
+    mbar_wait(full + st, ph);
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(stages + (size_t)st * p.stage_bytes);
+    for (int b = 0; b < nb; ++b) {
+      const long long s = (blk0 + b) * BLK + lane;
+      if (s < p.r1) {
+        const uint32_t* rowp = tile + (size_t)b * block_words + lane;
+        uint32_t T1, M1, T2, M2;
+        count_block_b32(rowp, p.W1, T1, M1);
+        count_block_b32(rowp + p.W1 * BLK, p.W2, T2, M2);
+        const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
+        const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
+        sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
       }
-      const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
-      const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
-      sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
     }
-    mbar_arrive(empty + st);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);
+    st += p.cwarps;
+    if (st >= p.nstage) { st -= p.nstage; ph ^= 1; }
   }
-  named_bar_sync(1, K1_ROWS);
-  sink_flush(p, sm, cta_group, tid, K1_ROWS);
+  named_bar_sync(1, K1_CONS);
+  sink_flush(p, sm, cta_group, tid, K1_CONS);
 }
 
 // ------------------------------------------------------------------------------------------------ K1 (counts entry)
@@ -435,7 +414,7 @@ __global__ void __launch_bounds__(K1C_THREADS) k1_counts(const __grid_constant__
     const long long row0 = p.r0 + t * K1C_THREADS;
     const long long s = row0 + tid;
     const int g0 = tile_group(p, row0, cc);
-    if (g0 != cta_group) {
+    if (g0 != cta_group) {  // uniform across the CTA: switch the privatised histograms to the new background group
       __syncthreads();
       sink_flush(p, sm, cta_group, tid, K1C_THREADS);
       __syncthreads();
@@ -579,8 +558,7 @@ __global__ void __launch_bounds__(256) k2_bounds_snp(const __grid_constant__ Win
 
 // ------------------------------------------------------------------------------------------------ K3+K4 scoring
 struct ScoreParams {
-  const uint32_t* key;
-  const uint32_t* alts;
+  const uint2* rec;
   const uint8_t* flags;
   const int32_t* wlo;
   const int32_t* whi;
@@ -654,11 +632,23 @@ __device__ __forceinline__ int folded_interior(int a, int n) {
   return (a != 0 && f >= 1 && f <= n - 1) ? f : 0;
 }
 
-// One warp per candidate window (<= WCAP SNPs).  Per-warp shared memory: open-addressing table of the window's
-// 2D bins (keys + counts), the slot of every SNP, and packed 16-bit 1D histograms.
+// One warp per candidate window (<= WCAP SNPs).  Per-warp shared memory: an open-addressing table of the window's 2D
+// bins (one word per slot: bin << 10 | multiplicity), the list of occupied slots, and packed 16-bit folded 1D histograms.
+//   pass 1 (per SNP)          insert the 2D bin, bump the two folded 1D bins
+//   pass 2 (per distinct bin) acc += x (ln x - ln b); the slot is cleared on the way
+//   pass 3 (per 1D bin pair)  same for both 1D spectra, bins cleared on the way
 constexpr int SCORE_WARPS = 8;
+constexpr int KEY_SHIFT = 10;  // multiplicity field (< 1024, WCAP = 768)
 __host__ __device__ inline int score_warp_smem_words(int n1, int n2) {
-  return HASH_SLOTS * 2 + WCAP / 2 + (n1 + 2) / 2 + (n2 + 2) / 2;
+  return HASH_SLOTS + WCAP / 2 + 2 + (n1 + 2) / 2 + (n2 + 2) / 2;
+}
+// limits of the per-warp scorer; panels beyond them are scored by the CTA kernel only
+__host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
+  return n1 <= 32767 && n2 <= 32767 && bins2d < (1 << (32 - KEY_SHIFT)) - 1;
+}
+
+__device__ __forceinline__ void acc_bin(double& acc, uint32_t x, const double* lnI, const double* lb, int k) {
+  if (x) acc = fma((double)x, __ldg(lnI + x) - __ldg(lb + k), acc);
 }
 
 __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p, int warps_per_cta) {
@@ -666,17 +656,20 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= warps_per_cta) return;
   const int wwords = score_warp_smem_words(p.n1, p.n2);
-  uint32_t* tkey = sm32 + (size_t)warp * wwords;
-  uint32_t* tcnt = tkey + HASH_SLOTS;
-  uint16_t* slot = reinterpret_cast<uint16_t*>(tcnt + HASH_SLOTS);
-  uint32_t* h1a = tcnt + HASH_SLOTS + WCAP / 2;  // packed 16-bit bins
-  uint32_t* h1b = h1a + (p.n1 + 2) / 2;
-  for (int i = lane; i < HASH_SLOTS; i += 32) { tkey[i] = EMPTY_KEY; tcnt[i] = 0; }
-  for (int i = lane; i < (p.n1 + 2) / 2 + (p.n2 + 2) / 2; i += 32) h1a[i] = 0;
+  uint32_t* tab = sm32 + (size_t)warp * wwords;
+  uint16_t* slist = reinterpret_cast<uint16_t*>(tab + HASH_SLOTS);
+  uint32_t* nd = tab + HASH_SLOTS + WCAP / 2;  // number of occupied slots
+  uint32_t* h1a = nd + 2;                      // packed 16-bit bins: bin f in word f >> 1, half f & 1
+  const int nw1 = (p.n1 + 2) / 2, nw2 = (p.n2 + 2) / 2;
+  uint32_t* h1b = h1a + nw1;
+  for (int i = lane; i < HASH_SLOTS; i += 32) tab[i] = EMPTY_KEY;
+  for (int i = lane; i < 2 + nw1 + nw2; i += 32) nd[i] = 0;
   __syncwarp();
+  const uint32_t last = (uint32_t)p.bins2d - 1;
+  const bool has_flags = p.flags != nullptr;
 
-  const long long nw = (long long)gridDim.x * warps_per_cta;
-  for (long long id = (long long)blockIdx.x * warps_per_cta + warp; id < p.ncand; id += nw) {
+  const long long nwarps = (long long)gridDim.x * warps_per_cta;
+  for (long long id = (long long)blockIdx.x * warps_per_cta + warp; id < p.ncand; id += nwarps) {
     const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
     const int cnt = hi - lo;
     if (cnt == 0) {
@@ -688,69 +681,71 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     const double* lb2 = p.lb2 + (long long)g * p.bins2d;
     const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
-    const uint32_t last = (uint32_t)p.bins2d - 1;
 
-    int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
-    double slb2 = 0.0, slb1a = 0.0, slb1b = 0.0;
-    // phase 1: insert
-    for (int base = 0; base < cnt; base += 32) {
-      const int i = base + lane;
-      if (i < cnt) {
-        const uint32_t k = __ldg(p.key + lo + i);
-        const uint32_t a = __ldg(p.alts + lo + i);
-        count += p.flags ? ((__ldg(p.flags + lo + i) >> 1) & 1) : 1;
-        nall += k != 0;
-        uint32_t sl = 0xFFFF;
-        if (k != 0 && k != last) {
-          uint32_t h = (k * 0x9E3779B1u) >> 22;  // 10 bits
-          while (true) {
-            const uint32_t prev = atomicCAS(tkey + h, EMPTY_KEY, k);
-            if (prev == EMPTY_KEY || prev == k) break;
-            h = (h + 1) & (HASH_SLOTS - 1);
+    // packed per-lane counters: N2 | N1a << 10 | N1b << 20  and  nall | count << 10  (warp totals <= WCAP < 1024)
+    uint32_t nn = 0, nc = 0;
+    // ---- pass 1
+#pragma unroll 2
+    for (int i = lane; i < cnt; i += 32) {
+      const uint2 r = __ldg(p.rec + lo + i);
+      const uint32_t k = r.x;
+      const uint32_t c1 = has_flags ? ((__ldg(p.flags + lo + i) >> 1) & 1u) : 1u;
+      nc += (k != 0) + (c1 << 10);
+      if (k != 0 && k != last) {
+        uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
+        while (true) {
+          uint32_t e = tab[h];
+          if (e == EMPTY_KEY) {
+            e = atomicCAS(tab + h, EMPTY_KEY, (k << KEY_SHIFT) | 1u);
+            if (e == EMPTY_KEY) { slist[atomicAdd(nd, 1u)] = (uint16_t)h; break; }
           }
-          atomicAdd(tcnt + h, 1u);
-          sl = h;
-          ++N2;
-          slb2 += __ldg(lb2 + k);
+          if ((e >> KEY_SHIFT) == k) { atomicAdd(tab + h, 1u); break; }
+          h = (h + 1) & (HASH_SLOTS - 1);
         }
-        slot[i] = (uint16_t)sl;
-        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
-        if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); ++N1a; slb1a += __ldg(lb1a + fa); }
-        if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); ++N1b; slb1b += __ldg(lb1b + fb); }
+        nn += 1u;
+      }
+      const int fa = folded_interior((int)(r.y & 0xFFFF), p.n1), fb = folded_interior((int)(r.y >> 16), p.n2);
+      if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); nn += 1u << 10; }
+      if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); nn += 1u << 20; }
+    }
+    __syncwarp();
+    // ---- pass 2: distinct 2D bins
+    double a2 = 0.0, a1a = 0.0, a1b = 0.0;
+    const int ndist = (int)*nd;
+#pragma unroll 2
+    for (int j = lane; j < ndist; j += 32) {
+      const uint32_t sl = slist[j];
+      const uint32_t e = tab[sl];
+      tab[sl] = EMPTY_KEY;
+      acc_bin(a2, e & ((1u << KEY_SHIFT) - 1), p.lnI, lb2, (int)(e >> KEY_SHIFT));
+    }
+    // ---- pass 3: folded 1D bins (two per word)
+    for (int w = lane; w < nw1; w += 32) {
+      const uint32_t v = h1a[w];
+      if (v) {
+        h1a[w] = 0;
+        acc_bin(a1a, v & 0xFFFF, p.lnI, lb1a, 2 * w);
+        acc_bin(a1a, v >> 16, p.lnI, lb1a, 2 * w + 1);
+      }
+    }
+    for (int w = lane; w < nw2; w += 32) {
+      const uint32_t v = h1b[w];
+      if (v) {
+        h1b[w] = 0;
+        acc_bin(a1b, v & 0xFFFF, p.lnI, lb1b, 2 * w);
+        acc_bin(a1b, v >> 16, p.lnI, lb1b, 2 * w + 1);
       }
     }
     __syncwarp();
-    // phase 2: multiplicities  sum_s ln m_s == sum_k x_k ln x_k
-    double slm2 = 0.0, slm1a = 0.0, slm1b = 0.0;
-    for (int base = 0; base < cnt; base += 32) {
-      const int i = base + lane;
-      if (i < cnt) {
-        const uint32_t sl = slot[i];
-        if (sl != 0xFFFF) slm2 += ln_mult(p, tcnt[sl]);
-        const uint32_t a = __ldg(p.alts + lo + i);
-        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
-        if (fa) slm1a += ln_mult(p, (h1a[fa >> 1] >> (16 * (fa & 1))) & 0xFFFF);
-        if (fb) slm1b += ln_mult(p, (h1b[fb >> 1] >> (16 * (fb & 1))) & 0xFFFF);
-      }
+    if (lane == 0) *nd = 0;
+    nn = __reduce_add_sync(0xffffffffu, nn);
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    a2 = warp_sum(a2); a1a = warp_sum(a1a); a1b = warp_sum(a1b);
+    if (lane == 0) {
+      const int N2 = nn & 0x3FF, N1a = (nn >> 10) & 0x3FF, N1b = nn >> 20;
+      write_result(p, id, (int)(nc >> 10), (int)(nc & 0x3FF), N2, N1a, N1b, a2, 0.0, a1a, 0.0, a1b, 0.0, p.B + g * 3);
     }
     __syncwarp();
-    // phase 3: clear only what was touched
-    for (int base = 0; base < cnt; base += 32) {
-      const int i = base + lane;
-      if (i < cnt) {
-        const uint32_t sl = slot[i];
-        if (sl != 0xFFFF) { tkey[sl] = EMPTY_KEY; tcnt[sl] = 0; }
-        const uint32_t a = __ldg(p.alts + lo + i);
-        const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
-        if (fa) h1a[fa >> 1] = 0;
-        if (fb) h1b[fb >> 1] = 0;
-      }
-    }
-    __syncwarp();
-    N2 = warp_sum(N2); N1a = warp_sum(N1a); N1b = warp_sum(N1b); nall = warp_sum(nall); count = warp_sum(count);
-    slb2 = warp_sum(slb2); slb1a = warp_sum(slb1a); slb1b = warp_sum(slb1b);
-    slm2 = warp_sum(slm2); slm1a = warp_sum(slm1a); slm1b = warp_sum(slm1b);
-    if (lane == 0) write_result(p, id, count, nall, N2, N1a, N1b, slm2, slb2, slm1a, slb1a, slm1b, slb1b, p.B + g * 3);
   }
 }
 
@@ -776,7 +771,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
     double slb2 = 0.0, slb1a = 0.0, slb1b = 0.0, slm2 = 0.0, slm1a = 0.0, slm1b = 0.0;
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint32_t k = p.key[s], a = p.alts[s];
+      const uint2 r = p.rec[s];
+      const uint32_t k = r.x, a = r.y;
       count += p.flags ? ((p.flags[s] >> 1) & 1) : 1;
       nall += k != 0;
       if (k != 0 && k != last) { atomicAdd(h2 + k, 1u); ++N2; slb2 += lb2[k]; }
@@ -786,7 +782,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     }
     __syncthreads();
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint32_t k = p.key[s], a = p.alts[s];
+      const uint2 r = p.rec[s];
+      const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) slm2 += ln_mult(p, __ldcg(h2 + k));
       const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
       if (fa) slm1a += ln_mult(p, __ldcg(h1a + fa));
@@ -794,7 +791,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     }
     __syncthreads();
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint32_t k = p.key[s], a = p.alts[s];
+      const uint2 r = p.rec[s];
+      const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) h2[k] = 0;
       const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
       if (fa) h1a[fa] = 0;
@@ -816,10 +814,9 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
 }
 
 // dense spectra of one window (calculate_2d_sfs / calculate_1d_sfs on window_data)
-__global__ void k_window_hist(const uint32_t* key, const uint32_t* alts, int lo, int hi, uint32_t* h2, uint32_t* h1a,
-                              uint32_t* h1b) {
+__global__ void k_window_hist(const uint2* rec, int lo, int hi, uint32_t* h2, uint32_t* h1a, uint32_t* h1b) {
   for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
-    const uint32_t k = key[s], a = alts[s];
+    const uint32_t k = rec[s].x, a = rec[s].y;
     if (k) atomicAdd(h2 + k, 1u);
     if (a & 0xFFFF) atomicAdd(h1a + (a & 0xFFFF), 1u);
     if (a >> 16) atomicAdd(h1b + (a >> 16), 1u);
@@ -877,10 +874,13 @@ __device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (
 __global__ void __launch_bounds__(256) k_synth(uint32_t* G, long long S, long long snp0, int W1, int W2, int ns1, int ns2,
                                                uint64_t seed, uint32_t miss_thr16, double fst) {
   const int RW = W1 + W2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= S * RW) return;
-  const long long row = idx / RW;
-  const int w = (int)(idx - row * RW);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // word index in the B32 layout
+  const long long nblk = (S + BLK - 1) / BLK;
+  if (idx >= nblk * RW * BLK) return;
+  const long long bw = idx / BLK;  // block * RW + word
+  const long long row = (bw / RW) * BLK + (idx & (BLK - 1));
+  const int w = (int)(bw % RW);
+  if (row >= S) { G[idx] = 0u; return; }
   const int pop = w >= W1;
   const int wi = pop ? w - W1 : w;
   const int ns = pop ? ns2 : ns1;

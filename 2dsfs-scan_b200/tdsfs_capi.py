@@ -19,7 +19,7 @@ EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
-    "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
+    "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_version",
 ]
 
@@ -95,9 +95,10 @@ class Handle:
             raise TdsfsError(rc, self._L.tdsfs_last_error().decode())
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            self._L.tdsfs_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.tdsfs_destroy(h)
+            self._h = None
 
     __del__ = close
 

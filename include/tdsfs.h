@@ -149,6 +149,9 @@ int tdsfs_scan_bp(tdsfs_t* ctx, int64_t W, tdsfs_result_t* out, int64_t cap, int
 int tdsfs_scan_snp(tdsfs_t* ctx, int64_t N, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
 int tdsfs_fetch_results(tdsfs_t* ctx, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
 
+/* Synchronise the stream and report deferred device-side errors (TDSFS_ERR_RANGE) after asynchronous calls. */
+int tdsfs_check(tdsfs_t* ctx);
+
 /* One-call convenience used by the end-to-end benchmark: background(mode) -> finalize -> scan_bp. */
 int tdsfs_run_bp(tdsfs_t* ctx, int32_t bg_mode, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
 
@@ -166,8 +169,9 @@ int tdsfs_likelihood(tdsfs_t* ctx, const int64_t* x, const double* b, int64_t n,
  * log-uniform, per-population drift, Binomial(2,p) calls, iid missing.  snp0 = global index of row 0. */
 int tdsfs_synth_genotypes(tdsfs_t* ctx, void* G_dev, int64_t S, int64_t snp0, int32_t words1, int32_t words2,
                           int32_t ns1, int32_t ns2, uint64_t seed, double missing_rate, double fst);
-/* CUDA-event times (ms) of the last background / scan call: [0]=count kernel (K1), [1]=finalize, [2]=boundaries,
- * [3]=score (small windows), [4]=score (large windows), [5]=whole background call, [6]=whole scan call. */
+/* CUDA-event times (ms) of the last background / finalize / scan calls (synchronises the stream):
+ * [0]=count kernel (K1), [1]=finalize, [2]=boundaries (K2), [3]=score small windows (K3/K4), [4]=score large windows,
+ * [5]=background call, [6]=scan call, [7]=K1 start -> last score kernel end. */
 int tdsfs_timings(tdsfs_t* ctx, float* ms, int32_t n);
 int64_t tdsfs_launch_count(tdsfs_t* ctx); /* kernels launched by this handle so far */
 int tdsfs_version(void);

@@ -146,7 +146,7 @@ def random_panel(rng, S, ns1, ns2, C, L, miss=0.03):
 def test_genotype_scan_vs_oracle(T, h, n1, n2, S, C, L, W, bg):
     rng = np.random.default_rng(n1 * 1000 + n2 + S)
     G, w1, w2, pos, off = random_panel(rng, S, n1, n2, C, L)
-    cnt = O.unpack_counts(G, w1, w2, n1, n2)
+    cnt = O.unpack_counts(G, w1, w2, n1, n2, S)
     h.set_panel(n1, n2, True)
     h.load_genotypes(G, S, w1, w2, n1, n2, pos, off)
     h.background(T.BG_PER_CHROM if bg == "per_chrom" else T.BG_GENOME)
@@ -170,7 +170,7 @@ def test_large_windows_and_unfolded(T, h):
     rng = np.random.default_rng(99)
     n1, n2, S = 30, 40, 50000
     G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 2, 1000000)
-    cnt = O.unpack_counts(G, w1, w2, n1, n2)
+    cnt = O.unpack_counts(G, w1, w2, n1, n2, S)
     for fold in (True, False):
         h.set_panel(n1, n2, fold)
         h.load_genotypes(G, S, w1, w2, n1, n2, pos, off)
@@ -187,7 +187,7 @@ def test_counts_entry_equals_genotype_entry_and_window_spectra(T, h):
     rng = np.random.default_rng(123)
     n1, n2, S = 25, 9, 8000
     G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 3, 90000)
-    cnt = O.unpack_counts(G, w1, w2, n1, n2)
+    cnt = O.unpack_counts(G, w1, w2, n1, n2, S)
     h.set_panel(n1, n2, True)
     h.load_genotypes(G, S, w1, w2, n1, n2, pos, off)
     a = h.run_bp(T.BG_GENOME, 4000)
@@ -210,7 +210,7 @@ def test_filters_flags_and_fixups(T, h):
     rng = np.random.default_rng(7)
     n1, n2, S = 12, 12, 6000
     G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 2, 80000)
-    cnt = O.unpack_counts(G, w1, w2, n1, n2)
+    cnt = O.unpack_counts(G, w1, w2, n1, n2, S)
     inc = rng.random(S) < 0.6
     cntb = rng.random(S) < 0.8
     flags = (inc.astype(np.uint8) | (cntb.astype(np.uint8) << 1))
@@ -282,18 +282,20 @@ def test_synthetic_generator_statistics(T, h):
     import torch
     S, ns1, ns2 = 4096, 200, 200
     w1 = w2 = 13
-    g = torch.zeros((S, w1 + w2), dtype=torch.int32, device="cuda")
+    g = torch.zeros(((S + 31) // 32 * (w1 + w2) * 32,), dtype=torch.int32, device="cuda")
     h.synth_genotypes(g.data_ptr(), S, 1000, w1, w2, ns1, ns2, 20241004)
     g2 = torch.zeros_like(g)
     h.synth_genotypes(g2.data_ptr(), S, 1000, w1, w2, ns1, ns2, 20241004)
     assert torch.equal(g, g2)
-    G = g.cpu().numpy().view(np.uint32)
+    from tdsfs_pack import from_b32
+    Gb = g.cpu().numpy().view(np.uint32)
+    G = from_b32(Gb, S, w1 + w2)
     codes = np.stack([(G >> (2 * i)) & 3 for i in range(16)], axis=-1).reshape(S, -1)
     pop1 = codes[:, :w1 * 16]
     assert (pop1[:, ns1:] == 0).all()
     miss = (pop1[:, :ns1] == 2).mean()
     assert 0.015 < miss < 0.025
-    cnt = O.unpack_counts(G, w1, w2, ns1, ns2)
+    cnt = O.unpack_counts(Gb, w1, w2, ns1, ns2, S)
     assert cnt.min() >= 0 and (cnt[:, 0] + cnt[:, 1] <= 2 * ns1).all()
     # spectrum is dominated by rare variants (log-uniform ancestral frequency)
     assert (cnt[:, 1] <= 40).mean() > 0.5
