@@ -1,6 +1,7 @@
 // tdsfs.cu -- C ABI of libtdsfs.so (see include/tdsfs.h) over the kernels in tdsfs_kernels.cuh.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -391,7 +392,7 @@ static int ensure_tables(tdsfs_ctx* c, int NG) {
   CKR(dev_alloc(&c->d_lb2, (long long)NG * c->bins2d));
   CKR(dev_alloc(&c->d_lb1a, (long long)NG * (c->n1 + 1)));
   CKR(dev_alloc(&c->d_lb1b, (long long)NG * (c->n2 + 1)));
-  CKR(dev_alloc(&c->d_B, (long long)NG * 3));
+  CKR(dev_alloc(&c->d_B, (long long)NG * 6));
   CKR(dev_alloc(&c->d_Bsum, (long long)NG * 3));
   c->table_groups = NG;
   return 0;
@@ -536,10 +537,11 @@ extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double*
   cudaStream_t st = c->stream;
   CKR(ensure_tables(c, 1));
   // interior totals summed on the host in index order, as the reference's sum(counts_bg) does (:665, :517)
-  double B[3] = {0, 0, 0};
+  double B[6] = {0, 0, 0, 0, 0, 0};
   for (int k = 1; k < c->bins2d - 1; ++k) B[0] += b2d[k];
   for (int k = 1; k <= c->n1 - 1; ++k) B[1] += b1a[k];
   for (int k = 1; k <= c->n2 - 1; ++k) B[2] += b1b[k];
+  for (int q = 0; q < 3; ++q) B[3 + q] = B[q] > 0.0 ? log(B[q]) : (B[q] == 0.0 ? -INFINITY : NAN);
   double *t2 = nullptr, *t1a = nullptr, *t1b = nullptr;
   CKR(dev_alloc(&t2, c->bins2d)); CKR(dev_alloc(&t1a, c->n1 + 1)); CKR(dev_alloc(&t1b, c->n2 + 1));
   CK(cudaMemcpyAsync(t2, b2d, (size_t)c->bins2d * 8, cudaMemcpyHostToDevice, st));
@@ -574,7 +576,7 @@ extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
   f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum;
   dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 4, (c->bins2d + 255) / 256)), (unsigned)c->NG);
   k_finalize_counts<<<grid, 256, 0, st>>>(f);
-  k_u64_to_double<<<(c->NG * 3 + 255) / 256, 256, 0, st>>>(c->d_Bsum, c->d_B, c->NG * 3);
+  k_u64_to_double<<<(c->NG * 3 + 255) / 256, 256, 0, st>>>(c->d_Bsum, c->d_B, c->NG);
   c->launches += 2;
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[EV_FIN1], st));

@@ -472,9 +472,14 @@ __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__
   }
 }
 
-__global__ void k_u64_to_double(const unsigned long long* in, double* out, int n) {
+// interior totals -> table [group][6] = B (2D, 1D pop1, 1D pop2) then ln B
+__global__ void k_u64_to_double(const unsigned long long* in, double* out, int ngroups) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (double)in[i];
+  if (i < ngroups * 3) {
+    const double b = (double)in[i];
+    out[(i / 3) * 6 + i % 3] = b;
+    out[(i / 3) * 6 + 3 + i % 3] = b > 0.0 ? log(b) : -INFINITY;
+  }
 }
 
 // precomputed (float) background: lb = ln b
@@ -569,7 +574,7 @@ struct ScoreParams {
   const double* lb2;
   const double* lb1a;
   const double* lb1b;
-  const double* B;       // [NG][3]
+  const double* B;       // [NG][6]: interior totals B (2D, 1D pop1, 1D pop2), then ln B
   const double* lnI;     // ln(m), m < LN_TABLE
   // outputs
   int32_t* r_count;
@@ -599,20 +604,21 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// T = 2 * ( sum_s ln m_s  -  sum_s ln b_key(s)  -  N (ln N - ln B) )   ==  2 (ll_fg - ll_bg) of the reference
-__device__ __forceinline__ double clr_value(int N, double slm, double slb, double B, bool& none) {
-  none = (N == 0) || !(B != 0.0);
+// T = 2 * ( sum_k x_k (ln x_k - ln b_k)  -  N (ln N - ln B) )   ==  2 (ll_fg - ll_bg) of the reference (:679-682)
+// acc = sum_k x_k (ln x_k - ln b_k); Bg = {B[3], lnB[3]} of the background group; q = 0 (2D), 1, 2 (1D pops)
+__device__ __forceinline__ double clr_value(const ScoreParams& p, int N, double acc, const double* Bg, int q, bool& none) {
+  const double B = __ldg(Bg + q);
+  none = (N == 0) || !(B != 0.0);  // the reference returns None (:645-647, :668-670)
   if (none) return NAN;
-  return 2.0 * (slm - slb - (double)N * (log((double)N) - log(B)));
+  return 2.0 * (acc - (double)N * (ln_mult(p, (uint32_t)N) - __ldg(Bg + 3 + q)));
 }
 
 __device__ __forceinline__ void write_result(const ScoreParams& p, long long id, int count, int nall, int N2, int N1a, int N1b,
-                                             double slm2, double slb2, double slm1a, double slb1a, double slm1b, double slb1b,
-                                             const double* Bg) {
+                                             double acc2, double acc1a, double acc1b, const double* Bg) {
   bool none2, none1a, none1b;
-  const double T2 = clr_value(N2, slm2, slb2, Bg[0], none2);
-  const double T1a = clr_value(N1a, slm1a, slb1a, Bg[1], none1a);
-  const double T1b = clr_value(N1b, slm1b, slb1b, Bg[2], none1b);
+  const double T2 = clr_value(p, N2, acc2, Bg, 0, none2);
+  const double T1a = clr_value(p, N1a, acc1a, Bg, 1, none1a);
+  const double T1b = clr_value(p, N1b, acc1b, Bg, 2, none1b);
   uint8_t f = (none2 ? TDSFS_F_T2D_NONE : 0) | (none1a ? TDSFS_F_T1D_P1_NONE : 0) | (none1b ? TDSFS_F_T1D_P2_NONE : 0);
   if (p.snp_mode && nall == 0) f |= TDSFS_F_SKIPPED;  // :1496 window skipped when its 2D spectrum sums to 0
   p.r_count[id] = count;
@@ -684,40 +690,54 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 
     // packed per-lane counters: N2 | N1a << 10 | N1b << 20  and  nall | count << 10  (warp totals <= WCAP < 1024)
     uint32_t nn = 0, nc = 0;
-    // ---- pass 1
-#pragma unroll 2
-    for (int i = lane; i < cnt; i += 32) {
-      const uint2 r = __ldg(p.rec + lo + i);
-      const uint32_t k = r.x;
-      const uint32_t c1 = has_flags ? ((__ldg(p.flags + lo + i) >> 1) & 1u) : 1u;
-      nc += (k != 0) + (c1 << 10);
-      if (k != 0 && k != last) {
-        uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
-        while (true) {
-          uint32_t e = tab[h];
-          if (e == EMPTY_KEY) {
-            e = atomicCAS(tab + h, EMPTY_KEY, (k << KEY_SHIFT) | 1u);
-            if (e == EMPTY_KEY) { slist[atomicAdd(nd, 1u)] = (uint16_t)h; break; }
-          }
-          if ((e >> KEY_SHIFT) == k) { atomicAdd(tab + h, 1u); break; }
-          h = (h + 1) & (HASH_SLOTS - 1);
-        }
-        nn += 1u;
+    // ---- pass 1: four records per lane in flight (the loads are independent of the table work)
+    for (int base = 0; base < cnt; base += 128) {
+      uint2 r[4];
+      uint32_t c1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + q * 32 + lane;
+        const bool in = i < cnt;
+        r[q] = in ? __ldg(p.rec + lo + i) : make_uint2(0u, 0u);
+        c1[q] = in ? (has_flags ? ((__ldg(p.flags + lo + i) >> 1) & 1u) : 1u) : 0u;
       }
-      const int fa = folded_interior((int)(r.y & 0xFFFF), p.n1), fb = folded_interior((int)(r.y >> 16), p.n2);
-      if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); nn += 1u << 10; }
-      if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); nn += 1u << 20; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t k = r[q].x;
+        nc += (k != 0) + (c1[q] << 10);
+        if (k != 0 && k != last) {
+          uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
+          while (true) {
+            uint32_t e = tab[h];
+            if (e == EMPTY_KEY) {
+              e = atomicCAS(tab + h, EMPTY_KEY, (k << KEY_SHIFT) | 1u);
+              if (e == EMPTY_KEY) { slist[atomicAdd(nd, 1u)] = (uint16_t)h; break; }
+            }
+            if ((e >> KEY_SHIFT) == k) { atomicAdd(tab + h, 1u); break; }
+            h = (h + 1) & (HASH_SLOTS - 1);
+          }
+          nn += 1u;
+        }
+        const int fa = folded_interior((int)(r[q].y & 0xFFFF), p.n1), fb = folded_interior((int)(r[q].y >> 16), p.n2);
+        if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); nn += 1u << 10; }
+        if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); nn += 1u << 20; }
+      }
     }
     __syncwarp();
-    // ---- pass 2: distinct 2D bins
+    // ---- pass 2: distinct 2D bins, two per lane in flight
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     const int ndist = (int)*nd;
-#pragma unroll 2
-    for (int j = lane; j < ndist; j += 32) {
-      const uint32_t sl = slist[j];
-      const uint32_t e = tab[sl];
-      tab[sl] = EMPTY_KEY;
-      acc_bin(a2, e & ((1u << KEY_SHIFT) - 1), p.lnI, lb2, (int)(e >> KEY_SHIFT));
+    for (int j = lane; j < ndist; j += 64) {
+      const bool two = j + 32 < ndist;
+      const uint32_t s0 = slist[j], s1 = two ? slist[j + 32] : 0u;
+      const uint32_t e0 = tab[s0], e1 = two ? tab[s1] : 0u;
+      tab[s0] = EMPTY_KEY;
+      if (two) tab[s1] = EMPTY_KEY;
+      const uint32_t x0 = e0 & ((1u << KEY_SHIFT) - 1), x1 = e1 & ((1u << KEY_SHIFT) - 1);
+      const double l0 = __ldg(lb2 + (e0 >> KEY_SHIFT)), l1 = two ? __ldg(lb2 + (e1 >> KEY_SHIFT)) : 0.0;
+      const double m0 = __ldg(p.lnI + x0), m1 = __ldg(p.lnI + x1);
+      a2 = fma((double)x0, m0 - l0, a2);
+      if (two) a2 = fma((double)x1, m1 - l1, a2);
     }
     // ---- pass 3: folded 1D bins (two per word)
     for (int w = lane; w < nw1; w += 32) {
@@ -741,9 +761,27 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     nn = __reduce_add_sync(0xffffffffu, nn);
     nc = __reduce_add_sync(0xffffffffu, nc);
     a2 = warp_sum(a2); a1a = warp_sum(a1a); a1b = warp_sum(a1b);
-    if (lane == 0) {
-      const int N2 = nn & 0x3FF, N1a = (nn >> 10) & 0x3FF, N1b = nn >> 20;
-      write_result(p, id, (int)(nc >> 10), (int)(nc & 0x3FF), N2, N1a, N1b, a2, 0.0, a1a, 0.0, a1b, 0.0, p.B + g * 3);
+    {  // lanes 0..2 finish one statistic each (table lookups only: ln N from the multiplicity table, ln B precomputed)
+      const int Nq = lane == 0 ? (int)(nn & 0x3FF) : (lane == 1 ? (int)((nn >> 10) & 0x3FF) : (int)(nn >> 20));
+      const double aq = lane == 0 ? a2 : (lane == 1 ? a1a : a1b);
+      bool none = false;
+      double Tq = 0.0;
+      if (lane < 3) Tq = clr_value(p, Nq, aq, p.B + g * 6, lane, none);
+      const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
+      if (lane == 0) {
+        uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
+        if (p.snp_mode && (nc & 0x3FF) == 0) f |= TDSFS_F_SKIPPED;
+        p.r_count[id] = (int)(nc >> 10);
+        p.r_flags[id] = f;
+        p.r_T2[id] = Tq;
+        p.r_n2[id] = Nq;
+      } else if (lane == 1) {
+        p.r_T1a[id] = Tq;
+        p.r_n1a[id] = Nq;
+      } else if (lane == 2) {
+        p.r_T1b[id] = Tq;
+        p.r_n1b[id] = Nq;
+      }
     }
     __syncwarp();
   }
@@ -807,7 +845,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     if (tid == 0) {
       for (int q = 0; q < 6; ++q) { double t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_d[q][x]; dv[q] = t; }
       for (int q = 0; q < 5; ++q) { int t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_i[q][x]; iv[q] = t; }
-      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[3], dv[0], dv[4], dv[1], dv[5], dv[2], p.B + g * 3);
+      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[3] - dv[0], dv[4] - dv[1], dv[5] - dv[2], p.B + g * 6);
     }
     __syncthreads();
   }
