@@ -468,12 +468,15 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
     p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile: >= one 32-SNP block, ~4-8 KB
     p.stage_bytes = p.tile_blocks * blk_bytes;
     // ring = k stages per consumer warp (k >= 2 when they fit): one being counted, the others in flight from HBM
-    const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 16);
+    const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
     if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
     p.cwarps = std::min(K1_CWARPS, fit);
-    p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));
-    const int smem = p.nstage * p.stage_bytes + p.nstage * 16 + hist_bytes;
-    CK(cudaFuncSetAttribute(k1_genotypes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));  // `depth` stages per warp
+    const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
+    void (*kern)(KeyParams) = k1_genotypes<0, 0>;
+    if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
+    else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     for (auto& ch : c->chunks) {
       if (ch.r1 <= ch.r0) continue;
       if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
@@ -481,7 +484,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
       const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
       const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
-      k1_genotypes<<<grid, K1_THREADS, smem, st>>>(p);
+      kern<<<grid, K1_THREADS, smem, st>>>(p);
       c->launches++;
     }
   } else {

@@ -19,9 +19,9 @@ namespace tdsfs {
 
 // ------------------------------------------------------------------------------------------------ constants
 constexpr int BLK = 32;               // SNPs per block of the block-transposed genotype layout ("B32")
-constexpr int K1_CWARPS = 12;         // consumer warps of the genotype count kernel (one 32-SNP block at a time each)
+constexpr int K1_CWARPS = 12;         // warps of the genotype count kernel (each runs its own TMA ring)
 constexpr int K1_CONS = K1_CWARPS * 32;
-constexpr int K1_THREADS = K1_CONS + 32;  // + one TMA producer warp
+constexpr int K1_THREADS = K1_CONS;
 constexpr int K1_ROWS = 128;          // row granularity of host-side upload chunks (multiple of BLK)
 constexpr int CORNER = 64;            // privatised low-count corner of the 2D background histogram (per CTA, smem)
 constexpr int H1CAP = 2048;           // privatised 1D bins per population (per CTA, smem)
@@ -164,9 +164,12 @@ struct PopCounts {
 
 // One population block of one SNP in the B32 layout: word w of the lane's SNP sits at blk[w * 32] (conflict-free LDS.32,
 // immediate offsets after unrolling).  Returns T = popcount of all bits, M = number of missing calls.
-__device__ __forceinline__ void count_block_b32(const uint32_t* blk, int W, uint32_t& T, uint32_t& M) {
+template <int TW>  // TW > 0: compile-time word count (fully unrolled, immediate offsets); TW == 0: runtime W
+__device__ __forceinline__ void count_block_b32(const uint32_t* blk, int Wrt, uint32_t& T, uint32_t& M) {
+  const int W = TW > 0 ? TW : Wrt;
   PopCounts pc;
   int w = 0;
+#pragma unroll
   for (; w + 8 <= W; w += 8) {
     const uint32_t* q = blk + w * BLK;
     uint4 a = make_uint4(q[0], q[BLK], q[2 * BLK], q[3 * BLK]);
@@ -302,28 +305,28 @@ __device__ __forceinline__ int tile_group(const KeyParams& p, long long row0, Ch
 }
 
 // ------------------------------------------------------------------------------------------------ K1 (genotypes)
-// One persistent CTA per SM.  Warp 16 = TMA producer: streams tiles of `tile_blocks` 32-SNP blocks (contiguous in the B32
-// layout) into a deep shared-memory ring with cp.async.bulk + mbarrier.  Warps 0-15 = consumers: tile i of the CTA goes to
-// warp i % 16; each lane owns one SNP of the block: bit-sliced popcount of its two population blocks straight from
-// shared memory (word w at +128 B: bank = lane), fold/key, one coalesced 8-byte record store, privatised histograms.
+// One persistent CTA per SM, 12 warps, no producer warp: every warp runs its OWN ring of `depth` TMA stages
+// (cp.async.bulk + one mbarrier per stage).  Tile i of the CTA (tile_blocks 32-SNP blocks, contiguous in the B32 layout)
+// belongs to warp i % cwarps; after counting a tile the warp's lane 0 refills the stage it just drained, so stages are
+// never blocked behind another warp.  Each lane owns one SNP of a block: bit-sliced popcount of its two population
+// blocks straight from shared memory (word w at +128 B: bank = lane), fold/key, one coalesced 8-byte record store,
+// privatised background histograms.
+template <int TW1, int TW2>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_constant__ KeyParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int RW = p.W1 + p.W2;
+  const int W1 = TW1 > 0 ? TW1 : p.W1, W2 = TW2 > 0 ? TW2 : p.W2;
+  const int RW = W1 + W2;
   uint8_t* stages = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
-  uint64_t* empty = full + p.nstage;
   SinkSmem sm;
-  sm.corner = reinterpret_cast<uint32_t*>(empty + p.nstage);
+  sm.corner = reinterpret_cast<uint32_t*>(full + p.nstage);
   sm.h1a = sm.corner + p.cr * p.cc;
   sm.h1b = sm.h1a + p.h1a;
   const int nhist = p.cr * p.cc + p.h1a + p.h1b;
 
   if (tid == 0) {
-    for (int i = 0; i < p.nstage; ++i) {
-      mbar_init(full + i, 1);
-      mbar_init(empty + i, 1);
-    }
+    for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
   }
   for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
@@ -334,63 +337,56 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
   const long long ntiles = (b1 - b0 + p.tile_blocks - 1) / p.tile_blocks;
   const long long t0 = ntiles * blockIdx.x / gridDim.x;
   const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const long long n = t1 - t0;
   const long long block_words = (long long)RW * BLK;
+  const int depth = p.nstage / p.cwarps;  // stages per warp
 
-  if (warp == K1_CWARPS) {
-    // ---------------- producer: one lane, one bulk copy per tile, ring position kept incrementally ----------------
-    if (lane == 0) {
-      const uint32_t full_bytes = (uint32_t)(p.tile_blocks * block_words * 4);
-      const uint32_t* src = p.G + (b0 + t0 * p.tile_blocks) * block_words;
-      const long long n = t1 - t0;
-      int st = 0;
-      uint32_t ph = 1;  // parity of the previous use of the stage (first pass: nothing to wait for)
-      for (long long i = 0; i < n; ++i) {
-        if (i >= p.nstage) mbar_wait(empty + st, ph);
-        uint32_t bytes = full_bytes;
-        if (i == n - 1) {  // the very last tile of the launch may be short
-          const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
-          bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
-        }
-        mbar_arrive_expect_tx(full + st, bytes);
-        bulk_g2s(stages + (size_t)st * p.stage_bytes, src, bytes, full + st);
-        src += (size_t)p.tile_blocks * block_words;
-        if (++st == p.nstage) { st = 0; ph ^= 1; }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumers ----------------
   ChromCache cc;
-  const int cta_group = (t1 > t0) ? tile_group(p, p.r0 + t0 * p.tile_blocks * BLK, cc) : -1;
-  // Stage st is always consumed by warp st % cwarps (nstage is a multiple of cwarps), so the warp that waits for use
-  // u+1 of a stage is the one that released use u: a parity wait can never alias a phase two uses away.
-  int st = warp;
-  uint32_t ph = 0;
-  for (long long i = warp; warp < p.cwarps && t0 + i < t1; i += p.cwarps) {
-    const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
-    const int nb = (int)min((long long)p.tile_blocks, b1 - blk0);
-    mbar_wait(full + st, ph);
-    const uint32_t* tile = reinterpret_cast<const uint32_t*>(stages + (size_t)st * p.stage_bytes);
-    for (int b = 0; b < nb; ++b) {
-      const long long s = (blk0 + b) * BLK + lane;
-      if (s < p.r1) {
-        const uint32_t* rowp = tile + (size_t)b * block_words + lane;
-        uint32_t T1, M1, T2, M2;
-        count_block_b32(rowp, p.W1, T1, M1);
-        count_block_b32(rowp + p.W1 * BLK, p.W2, T2, M2);
-        const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
-        const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
-        sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+  const int cta_group = (n > 0) ? tile_group(p, p.r0 + t0 * p.tile_blocks * BLK, cc) : -1;
+  if (warp < p.cwarps) {
+    uint8_t* my_stages = stages + (size_t)warp * depth * p.stage_bytes;
+    uint64_t* my_full = full + warp * depth;
+    auto issue = [&](long long i, int slot) {  // lane 0 only
+      const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+      const uint32_t bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
+      mbar_arrive_expect_tx(my_full + slot, bytes);
+      bulk_g2s(my_stages + (size_t)slot * p.stage_bytes, p.G + blk0 * block_words, bytes, my_full + slot);
+    };
+    if (lane == 0)
+      for (int j = 0; j < depth; ++j)
+        if (warp + (long long)j * p.cwarps < n) issue(warp + (long long)j * p.cwarps, j);
+    int slot = 0;
+    uint32_t ph = 0;
+    for (long long i = warp; i < n; i += p.cwarps) {
+      const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+      const int nb = (int)min((long long)p.tile_blocks, b1 - blk0);
+      mbar_wait(my_full + slot, ph);
+      const uint32_t* tile = reinterpret_cast<const uint32_t*>(my_stages + (size_t)slot * p.stage_bytes);
+      for (int b = 0; b < nb; ++b) {
+        const long long s = (blk0 + b) * BLK + lane;
+        if (s < p.r1) {
+          const uint32_t* rowp = tile + (size_t)b * block_words + lane;
+          uint32_t T1, M1, T2, M2;
+          count_block_b32<TW1>(rowp, W1, T1, M1);
+          count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
+          const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
+          const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
+          sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+        }
       }
+      __syncwarp();
+      if (lane == 0) {
+        const long long nxt = i + (long long)depth * p.cwarps;
+        if (nxt < n) {
+          fence_proxy_async();  // order this warp's generic-proxy reads of the stage before the async-proxy refill
+          issue(nxt, slot);
+        }
+      }
+      if (++slot == depth) { slot = 0; ph ^= 1; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + st);
-    st += p.cwarps;
-    if (st >= p.nstage) { st -= p.nstage; ph ^= 1; }
   }
-  named_bar_sync(1, K1_CONS);
-  sink_flush(p, sm, cta_group, tid, K1_CONS);
+  __syncthreads();
+  sink_flush(p, sm, cta_group, tid, K1_THREADS);
 }
 
 // ------------------------------------------------------------------------------------------------ K1 (counts entry)
