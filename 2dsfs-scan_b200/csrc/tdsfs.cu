@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,6 +89,7 @@ struct tdsfs_ctx {
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
   bool float_bg = false, tables_ready = false, fin_timed = false;
+  int score_group_warps = 2;  // warps per window in the shared-memory scorer (1, 2 or 4)
   int* d_err = nullptr;
   // windows / results
   long long ncand = 0, cand_cap = 0;
@@ -698,17 +700,23 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
     // small windows: one warp each
     if (!score_small_ok(c->n1, c->n2, c->bins2d)) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer (n <= 1023 per population)");
-    const int wwords = score_warp_smem_words(c->n1, c->n2);
-    int warps = std::min(SCORE_WARPS, (200 * 1024) / (wwords * 4));
-    if (warps < 1) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer");
-    const int smem = warps * wwords * 4;
-    CK(cudaFuncSetAttribute(k3_score_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // groups of G warps per window; G = 4 keeps the shared-memory footprint per window and quadruples the resident warps
+    const int gwords = score_group_smem_words(c->n1, c->n2);
+    if (gwords * 4 > 220 * 1024) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer");
+    int G = c->score_group_warps;
+    if (const char* e = getenv("TDSFS_SCORE_G")) G = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);  // tuning knob
+    while (G > 1 && (SCORE_WARPS / G) * gwords * 4 * 1 > 220 * 1024) G /= 2;
+    int groups = SCORE_WARPS / G;
+    while (groups > 1 && groups * gwords * 4 > 220 * 1024) groups /= 2;  // (only for very large panels)
+    const int smem = (SCORE_WARPS / G) * gwords * 4;
+    void (*sk)(ScoreParams) = G == 4 ? k3_score_small<4> : (G == 2 ? k3_score_small<2> : k3_score_small<1>);
+    CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_score_small, SCORE_WARPS * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sk, SCORE_WARPS * 32, smem));
     occ = std::max(1, occ);
-    const long long want = (ncand + warps - 1) / warps;
+    const long long want = (ncand + (SCORE_WARPS / G) - 1) / (SCORE_WARPS / G);
     const int grid = (int)std::min<long long>(want, (long long)c->sm_count * occ);
-    k3_score_small<<<grid, SCORE_WARPS * 32, smem, st>>>(s, warps);
+    sk<<<grid, SCORE_WARPS * 32, smem, st>>>(s);
     c->launches++;
     CK(cudaEventRecord(c->ev[EV_K3S], st));
     // large windows: one CTA each over dense global scratch
@@ -779,7 +787,9 @@ extern "C" int tdsfs_window_spectra(tdsfs_t* c, int64_t window, uint64_t* s2, ui
   CKR(dev_alloc(&d, words));
   CK(cudaMemsetAsync(d, 0, (size_t)words * 4, st));
   if (hi > lo) {
-    k_window_hist<<<std::min(1024, (hi - lo + 255) / 256), 256, 0, st>>>(c->d_rec, lo, hi, d, d + c->bins2d, d + c->bins2d + c->R1);
+    KeyParams kp;
+    fill_key_params(c, kp);
+    k_window_hist<<<std::min(1024, (hi - lo + 255) / 256), 256, 0, st>>>(kp, lo, hi, d, d + c->bins2d, d + c->bins2d + c->R1);
     c->launches++;
   }
   std::vector<uint32_t> h((size_t)words);

@@ -41,7 +41,7 @@ struct KeyParams {
   const tdsfs_fixup_t* fix;
   long long nfix;
   uint2* rec;         // per SNP: x = folded 2D bin index a1'*(2n2+1)+a2' (0 = contributes nothing),
-                      //          y = raw alt1 | raw alt2 << 16 (0 when filtered out)
+                      //          y = fa | fb << 16: folded 1D bins of pop1 / pop2 that enter the 1D likelihoods (0 = none)
   uint32_t* hist;     // [group][bins2d | R1 | R2]
   long long gstride;
   const int32_t* bg_group;  // per chromosome -> background group, -1 = not in any background; NULL = uniform_group
@@ -228,25 +228,36 @@ __device__ __forceinline__ int group_of_row(const KeyParams& p, long long s, Chr
   return g;
 }
 
+// 1D helper: folded bin of a raw alt count, 0 when the SNP does not enter the 1D likelihood
+// (alt == 0 skipped :430; folded bins 0 and n dropped :488)
+__device__ __forceinline__ int folded_interior(int a, int n) {
+  int f = min(a, 2 * n - a);
+  return (a != 0 && f >= 1 && f <= n - 1) ? f : 0;
+}
+
+// snp_flags handling shared by the count kernels: returns whether the SNP passes the spectrum filters (bit0) and
+// applies the sparse half-call corrections of rows flagged with bit2 (binary search in the sorted fix-up list).
+__device__ __forceinline__ bool row_filters(const KeyParams& p, long long s, int& ref1, int& alt1, int& ref2, int& alt2) {
+  if (!p.flags) return true;
+  const uint8_t f = __ldg(p.flags + s);
+  if (f & 4) {
+    long long lo = 0, hi = p.nfix;
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (p.fix[mid].snp < s) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < p.nfix && p.fix[lo].snp == s; ++lo) {
+      if (p.fix[lo].pop == 0) { ref1 += p.fix[lo].dref; alt1 += p.fix[lo].dalt; }
+      else { ref2 += p.fix[lo].dref; alt2 += p.fix[lo].dalt; }
+    }
+  }
+  return (f & 1) != 0;
+}
+
 // From the four counts of a SNP to its keys, the output arrays and the background histograms.
 __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int ref1, int alt1, int ref2, int alt2, int cta_group,
                                          const SinkSmem& sm, ChromCache& cc) {
-  bool include = true;
-  if (p.flags) {
-    uint8_t f = __ldg(p.flags + s);
-    include = (f & 1) != 0;
-    if (f & 4) {  // sparse half-call corrections: binary search the sorted fix-up list
-      long long lo = 0, hi = p.nfix;
-      while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (p.fix[mid].snp < s) lo = mid + 1; else hi = mid;
-      }
-      for (; lo < p.nfix && p.fix[lo].snp == s; ++lo) {
-        if (p.fix[lo].pop == 0) { ref1 += p.fix[lo].dref; alt1 += p.fix[lo].dalt; }
-        else { ref2 += p.fix[lo].dref; alt2 += p.fix[lo].dalt; }
-      }
-    }
-  }
+  const bool include = row_filters(p, s, ref1, alt1, ref2, alt2);
   uint32_t key = 0, alts = 0;
   if (include) {
     int k1 = alt1, k2 = alt2;
@@ -256,7 +267,7 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
       atomicOr(p.err, 1);
     } else {
       key = (uint32_t)(k1 * p.C2 + k2);  // (0,0) -> 0 : skipped SNP (:212)
-      alts = (uint32_t)alt1 | ((uint32_t)alt2 << 16);
+      alts = (uint32_t)folded_interior(alt1, p.n1) | ((uint32_t)folded_interior(alt2, p.n2) << 16);
       int g = group_of_row(p, s, cc);
       if (g >= 0) {
         uint32_t* gh = p.hist + (long long)g * p.gstride;
@@ -627,24 +638,21 @@ __device__ __forceinline__ void write_result(const ScoreParams& p, long long id,
   p.r_flags[id] = f;
 }
 
-// 1D helper: folded bin of a raw alt count, 0 when the SNP does not enter the 1D likelihood
-// (alt == 0 skipped :430; folded bins 0 and n dropped :488)
-__device__ __forceinline__ int folded_interior(int a, int n) {
-  int f = min(a, 2 * n - a);
-  return (a != 0 && f >= 1 && f <= n - 1) ? f : 0;
-}
-
-// One warp per candidate window (<= WCAP SNPs).  Per-warp shared memory: an open-addressing table of the window's 2D
-// bins (one word per slot: bin << 10 | multiplicity), the list of occupied slots, and packed 16-bit folded 1D histograms.
-//   pass 1 (per SNP)          insert the 2D bin, bump the two folded 1D bins
+// A group of G warps per candidate window (<= WCAP SNPs), 8 warps per CTA.  Per-group shared memory: an open-addressing
+// table of the window's 2D bins (one word per slot: bin << 10 | multiplicity), the list of occupied slots, packed
+// 16-bit folded 1D histograms and a small reduction scratch.
+//   pass 1 (per SNP)          insert the 2D bin, bump the two folded 1D bins      (all records of a thread in flight)
 //   pass 2 (per distinct bin) acc += x (ln x - ln b); the slot is cleared on the way
 //   pass 3 (per 1D bin pair)  same for both 1D spectra, bins cleared on the way
+// Several warps per window keep the same shared-memory footprint per window but multiply the resident warps, which is
+// what hides the shared-atomic and gather latencies.
 constexpr int SCORE_WARPS = 8;
 constexpr int KEY_SHIFT = 10;  // multiplicity field (< 1024, WCAP = 768)
-__host__ __device__ inline int score_warp_smem_words(int n1, int n2) {
-  return HASH_SLOTS + WCAP / 2 + 2 + (n1 + 2) / 2 + (n2 + 2) / 2;
+__host__ __device__ inline int score_group_smem_words(int n1, int n2) {
+  // table | slot list | counter | 1D bins (padded to an even word count) | reduction scratch (4 warps x 10 words)
+  return HASH_SLOTS + WCAP / 2 + 2 + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + 4 * 10;
 }
-// limits of the per-warp scorer; panels beyond them are scored by the CTA kernel only
+// limits of the shared-memory scorer; panels beyond them are scored by the CTA kernel only
 __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
   return n1 <= 32767 && n2 <= 32767 && bins2d < (1 << (32 - KEY_SHIFT)) - 1;
 }
@@ -653,29 +661,36 @@ __device__ __forceinline__ void acc_bin(double& acc, uint32_t x, const double* l
   if (x) acc = fma((double)x, __ldg(lnI + x) - __ldg(lb + k), acc);
 }
 
-__global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p, int warps_per_cta) {
+template <int G>
+__global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p) {
   extern __shared__ __align__(16) uint32_t sm32[];
+  constexpr int GT = G * 32;                 // threads per group
+  constexpr int GROUPS = SCORE_WARPS / G;    // groups per CTA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp >= warps_per_cta) return;
-  const int wwords = score_warp_smem_words(p.n1, p.n2);
-  uint32_t* tab = sm32 + (size_t)warp * wwords;
+  const int grp = warp / G, wg = warp % G, tg = wg * 32 + lane;
+  const int gwords = score_group_smem_words(p.n1, p.n2);
+  uint32_t* tab = sm32 + (size_t)grp * gwords;
   uint16_t* slist = reinterpret_cast<uint16_t*>(tab + HASH_SLOTS);
   uint32_t* nd = tab + HASH_SLOTS + WCAP / 2;  // number of occupied slots
   uint32_t* h1a = nd + 2;                      // packed 16-bit bins: bin f in word f >> 1, half f & 1
   const int nw1 = (p.n1 + 2) / 2, nw2 = (p.n2 + 2) / 2;
   uint32_t* h1b = h1a + nw1;
-  for (int i = lane; i < HASH_SLOTS; i += 32) tab[i] = EMPTY_KEY;
-  for (int i = lane; i < 2 + nw1 + nw2; i += 32) nd[i] = 0;
-  __syncwarp();
+  uint32_t* red = h1a + ((nw1 + nw2 + 1) & ~1);  // [4][10] (8-byte aligned): per warp {a2, a1a, a1b (doubles), N-pack, count, nall}
+  auto gsync = [&]() {
+    if (G == 1) __syncwarp(); else named_bar_sync(1 + grp, GT);
+  };
+  for (int i = tg; i < HASH_SLOTS; i += GT) tab[i] = EMPTY_KEY;
+  for (int i = tg; i < 2 + nw1 + nw2; i += GT) nd[i] = 0;
+  gsync();
   const uint32_t last = (uint32_t)p.bins2d - 1;
   const bool has_flags = p.flags != nullptr;
 
-  const long long nwarps = (long long)gridDim.x * warps_per_cta;
-  for (long long id = (long long)blockIdx.x * warps_per_cta + warp; id < p.ncand; id += nwarps) {
+  const long long ngroups = (long long)gridDim.x * GROUPS;
+  for (long long id = (long long)blockIdx.x * GROUPS + grp; id < p.ncand; id += ngroups) {
     const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
     const int cnt = hi - lo;
     if (cnt == 0) {
-      if (lane == 0) { p.r_count[id] = 0; p.r_flags[id] = TDSFS_F_EMPTY; }
+      if (tg == 0) { p.r_count[id] = 0; p.r_flags[id] = TDSFS_F_EMPTY; }
       continue;
     }
     if (cnt > WCAP) continue;  // scored by k3_score_large
@@ -684,23 +699,20 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
 
-    // packed per-lane counters: N2 | N1a << 10 | N1b << 20  and  nall | count << 10  (warp totals <= WCAP < 1024)
-    uint32_t nn = 0, nc = 0;
-    // ---- pass 1: four records per lane in flight (the loads are independent of the table work)
-    for (int base = 0; base < cnt; base += 128) {
+    // ---- pass 1: up to four records per thread in flight (the loads are independent of the table work)
+    int count = 0, nall = 0;
+    for (int base = 0; base < cnt; base += 4 * GT) {
       uint2 r[4];
-      uint32_t c1[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int i = base + q * 32 + lane;
-        const bool in = i < cnt;
-        r[q] = in ? __ldg(p.rec + lo + i) : make_uint2(0u, 0u);
-        c1[q] = in ? (has_flags ? ((__ldg(p.flags + lo + i) >> 1) & 1u) : 1u) : 0u;
+        const int i = base + q * GT + tg;
+        r[q] = i < cnt ? __ldg(p.rec + lo + i) : make_uint2(0u, 0u);
+        if (has_flags && i < cnt) count += (__ldg(p.flags + lo + i) >> 1) & 1;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t k = r[q].x;
-        nc += (k != 0) + (c1[q] << 10);
+        if (p.snp_mode) nall += k != 0;
         if (k != 0 && k != last) {
           uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
           while (true) {
@@ -712,20 +724,20 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
             if ((e >> KEY_SHIFT) == k) { atomicAdd(tab + h, 1u); break; }
             h = (h + 1) & (HASH_SLOTS - 1);
           }
-          nn += 1u;
         }
-        const int fa = folded_interior((int)(r[q].y & 0xFFFF), p.n1), fb = folded_interior((int)(r[q].y >> 16), p.n2);
-        if (fa) { atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1))); nn += 1u << 10; }
-        if (fb) { atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1))); nn += 1u << 20; }
+        const uint32_t fa = r[q].y & 0xFFFF, fb = r[q].y >> 16;
+        if (fa) atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1)));
+        if (fb) atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1)));
       }
     }
-    __syncwarp();
-    // ---- pass 2: distinct 2D bins, two per lane in flight
+    gsync();
+    // ---- pass 2: distinct 2D bins, two per thread in flight
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
+    uint32_t N2 = 0, N1a = 0, N1b = 0;
     const int ndist = (int)*nd;
-    for (int j = lane; j < ndist; j += 64) {
-      const bool two = j + 32 < ndist;
-      const uint32_t s0 = slist[j], s1 = two ? slist[j + 32] : 0u;
+    for (int j = tg; j < ndist; j += 2 * GT) {
+      const bool two = j + GT < ndist;
+      const uint32_t s0 = slist[j], s1 = two ? slist[j + GT] : 0u;
       const uint32_t e0 = tab[s0], e1 = two ? tab[s1] : 0u;
       tab[s0] = EMPTY_KEY;
       if (two) tab[s1] = EMPTY_KEY;
@@ -734,30 +746,52 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
       const double m0 = __ldg(p.lnI + x0), m1 = __ldg(p.lnI + x1);
       a2 = fma((double)x0, m0 - l0, a2);
       if (two) a2 = fma((double)x1, m1 - l1, a2);
+      N2 += x0 + x1;
     }
     // ---- pass 3: folded 1D bins (two per word)
-    for (int w = lane; w < nw1; w += 32) {
+    for (int w = tg; w < nw1; w += GT) {
       const uint32_t v = h1a[w];
       if (v) {
         h1a[w] = 0;
         acc_bin(a1a, v & 0xFFFF, p.lnI, lb1a, 2 * w);
         acc_bin(a1a, v >> 16, p.lnI, lb1a, 2 * w + 1);
+        N1a += (v & 0xFFFF) + (v >> 16);
       }
     }
-    for (int w = lane; w < nw2; w += 32) {
+    for (int w = tg; w < nw2; w += GT) {
       const uint32_t v = h1b[w];
       if (v) {
         h1b[w] = 0;
         acc_bin(a1b, v & 0xFFFF, p.lnI, lb1b, 2 * w);
         acc_bin(a1b, v >> 16, p.lnI, lb1b, 2 * w + 1);
+        N1b += (v & 0xFFFF) + (v >> 16);
       }
     }
-    __syncwarp();
-    if (lane == 0) *nd = 0;
-    nn = __reduce_add_sync(0xffffffffu, nn);
-    nc = __reduce_add_sync(0xffffffffu, nc);
+    // ---- reduce: warp level, then across the group's warps through shared memory
+    // N2 | N1a << 10 | N1b << 20 : every total is <= WCAP < 1024
+    uint32_t nn = __reduce_add_sync(0xffffffffu, N2 | (N1a << 10) | (N1b << 20));
+    if (has_flags) count = __reduce_add_sync(0xffffffffu, count);
+    if (p.snp_mode) nall = __reduce_add_sync(0xffffffffu, nall);
     a2 = warp_sum(a2); a1a = warp_sum(a1a); a1b = warp_sum(a1b);
-    {  // lanes 0..2 finish one statistic each (table lookups only: ln N from the multiplicity table, ln B precomputed)
+    if (G > 1) {
+      if (lane == 0) {
+        double* rd = reinterpret_cast<double*>(red + wg * 10);
+        rd[0] = a2; rd[1] = a1a; rd[2] = a1b;
+        red[wg * 10 + 6] = nn; red[wg * 10 + 7] = (uint32_t)count; red[wg * 10 + 8] = (uint32_t)nall;
+      }
+      gsync();
+      if (wg == 0) {
+        a2 = a1a = a1b = 0.0; nn = 0; count = 0; nall = 0;
+#pragma unroll
+        for (int w = 0; w < G; ++w) {
+          const double* rd = reinterpret_cast<const double*>(red + w * 10);
+          a2 += rd[0]; a1a += rd[1]; a1b += rd[2];
+          nn += red[w * 10 + 6]; count += (int)red[w * 10 + 7]; nall += (int)red[w * 10 + 8];
+        }
+      }
+    }
+    if (wg == 0) {  // lanes 0..2 finish one statistic each (ln N from the multiplicity table, ln B precomputed)
+      if (!has_flags) count = cnt;
       const int Nq = lane == 0 ? (int)(nn & 0x3FF) : (lane == 1 ? (int)((nn >> 10) & 0x3FF) : (int)(nn >> 20));
       const double aq = lane == 0 ? a2 : (lane == 1 ? a1a : a1b);
       bool none = false;
@@ -766,11 +800,12 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
       const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
       if (lane == 0) {
         uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
-        if (p.snp_mode && (nc & 0x3FF) == 0) f |= TDSFS_F_SKIPPED;
-        p.r_count[id] = (int)(nc >> 10);
+        if (p.snp_mode && nall == 0) f |= TDSFS_F_SKIPPED;
+        p.r_count[id] = count;
         p.r_flags[id] = f;
         p.r_T2[id] = Tq;
         p.r_n2[id] = Nq;
+        *nd = 0;
       } else if (lane == 1) {
         p.r_T1a[id] = Tq;
         p.r_n1a[id] = Nq;
@@ -779,7 +814,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
         p.r_n1b[id] = Nq;
       }
     }
-    __syncwarp();
+    gsync();
   }
 }
 
@@ -810,7 +845,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
       count += p.flags ? ((p.flags[s] >> 1) & 1) : 1;
       nall += k != 0;
       if (k != 0 && k != last) { atomicAdd(h2 + k, 1u); ++N2; slb2 += lb2[k]; }
-      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
       if (fa) { atomicAdd(h1a + fa, 1u); ++N1a; slb1a += lb1a[fa]; }
       if (fb) { atomicAdd(h1b + fb, 1u); ++N1b; slb1b += lb1b[fb]; }
     }
@@ -819,7 +854,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
       const uint2 r = p.rec[s];
       const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) slm2 += ln_mult(p, __ldcg(h2 + k));
-      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
       if (fa) slm1a += ln_mult(p, __ldcg(h1a + fa));
       if (fb) slm1b += ln_mult(p, __ldcg(h1b + fb));
     }
@@ -828,7 +863,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
       const uint2 r = p.rec[s];
       const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) h2[k] = 0;
-      const int fa = folded_interior((int)(a & 0xFFFF), p.n1), fb = folded_interior((int)(a >> 16), p.n2);
+      const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
       if (fa) h1a[fa] = 0;
       if (fb) h1b[fb] = 0;
     }
@@ -847,13 +882,32 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
   }
 }
 
-// dense spectra of one window (calculate_2d_sfs / calculate_1d_sfs on window_data)
-__global__ void k_window_hist(const uint2* rec, int lo, int hi, uint32_t* h2, uint32_t* h1a, uint32_t* h1b) {
-  for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
-    const uint32_t k = rec[s].x, a = rec[s].y;
+// dense spectra of one window (calculate_2d_sfs / calculate_1d_sfs on window_data): 2D bins from the stored records,
+// raw (unfolded) 1D alt counts recomputed from the source rows (counts entry or B32 genotype matrix)
+__global__ void k_window_hist(const __grid_constant__ KeyParams p, int lo, int hi, uint32_t* h2, uint32_t* h1a, uint32_t* h1b) {
+  const int RW = p.W1 + p.W2;
+  for (long long s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
+    const uint32_t k = p.rec[s].x;
     if (k) atomicAdd(h2 + k, 1u);
-    if (a & 0xFFFF) atomicAdd(h1a + (a & 0xFFFF), 1u);
-    if (a >> 16) atomicAdd(h1b + (a >> 16), 1u);
+    int ref1, alt1, ref2, alt2;
+    if (p.cnt) {
+      const uint2 v = reinterpret_cast<const uint2*>(p.cnt)[s];
+      ref1 = v.x & 0xFFFF; alt1 = v.x >> 16; ref2 = v.y & 0xFFFF; alt2 = v.y >> 16;
+    } else {
+      const uint32_t* row = p.G + ((s >> 5) * RW) * BLK + (s & 31);
+      int T[2] = {0, 0}, M[2] = {0, 0};
+      for (int w = 0; w < RW; ++w) {
+        const uint32_t x = row[(long long)w * BLK];
+        T[w >= p.W1] += __popc(x);
+        M[w >= p.W1] += __popc((x >> 1) & ~x & 0x55555555u);
+      }
+      alt1 = T[0] - M[0]; alt2 = T[1] - M[1];
+      ref1 = 2 * (p.ns1 - M[0]) - alt1; ref2 = 2 * (p.ns2 - M[1]) - alt2;
+    }
+    if (row_filters(p, s, ref1, alt1, ref2, alt2)) {
+      if (alt1 > 0 && alt1 < p.R1) atomicAdd(h1a + alt1, 1u);
+      if (alt2 > 0 && alt2 < p.R2) atomicAdd(h1b + alt2, 1u);
+    }
   }
 }
 
