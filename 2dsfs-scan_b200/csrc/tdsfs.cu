@@ -239,6 +239,12 @@ extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold)
   c->R1 = 2 * n1 + 1; c->R2 = 2 * n2 + 1; c->bins2d = (int)bins;
   c->keys_ready = c->tables_ready = c->results_ready = false;
   c->bg_mode = -1;
+  // everything sized by the spectrum shape is rebuilt for the new panel
+  dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum);
+  c->table_groups = 0;
+  dev_free(c->d_scratch);
+  dev_free(c->d_hist);
+  c->hist_words = 0;
   return 0;
 }
 
@@ -824,6 +830,26 @@ extern "C" int tdsfs_likelihood(tdsfs_t* c, const int64_t* x, const double* b, i
   CK(cudaStreamSynchronize(st));
   *flag = hf;
   cudaFree(dx); cudaFree(db); cudaFree(dout); cudaFree(dflag);
+  return 0;
+}
+
+extern "C" int tdsfs_poisson_score(tdsfs_t* c, const int64_t* x, const double* mu, int64_t n, double* score) {
+  if (!c || !score || n < 0 || (n > 0 && (!x || !mu))) return fail(TDSFS_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  long long* dx = nullptr;
+  double *dm = nullptr, *dout = nullptr;
+  CKR(dev_alloc(&dx, n)); CKR(dev_alloc(&dm, n)); CKR(dev_alloc(&dout, 1));
+  if (n) {
+    CK(cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dm, mu, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  }
+  k_poisson<<<1, 256, 0, st>>>(dx, dm, n, dout);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(score, dout, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dx); cudaFree(dm); cudaFree(dout);
   return 0;
 }
 

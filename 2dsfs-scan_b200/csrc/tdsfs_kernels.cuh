@@ -617,7 +617,10 @@ __device__ __forceinline__ double clr_value(const ScoreParams& p, int N, double 
   const double B = __ldg(Bg + q);
   none = (N == 0) || !(B != 0.0);  // the reference returns None (:645-647, :668-670)
   if (none) return NAN;
-  return 2.0 * (acc - (double)N * (ln_mult(p, (uint32_t)N) - __ldg(Bg + 3 + q)));
+  // explicit roundings (no FMA contraction): a window whose only populated bin is the only background bin, or a window
+  // that is its own background, must give exactly 0.0 like the reference -- its truthiness drives the stale-carry quirk
+  const double t = __dsub_rn(ln_mult(p, (uint32_t)N), __ldg(Bg + 3 + q));
+  return 2.0 * __dsub_rn(acc, __dmul_rn((double)N, t));
 }
 
 __device__ __forceinline__ void write_result(const ScoreParams& p, long long id, int count, int nall, int N2, int N1a, int N1b,
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 // One CTA per large window; dense scratch histograms in global memory (L2 resident), cleared by re-walking the window.
 constexpr int LARGE_THREADS = 256;
 __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_constant__ ScoreParams p) {
-  __shared__ double red_d[6][LARGE_THREADS / 32];
+  __shared__ double red_d[3][LARGE_THREADS / 32];
   __shared__ int red_i[5][LARGE_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nl = *p.nlarge;
@@ -838,45 +841,46 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
     int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
-    double slb2 = 0.0, slb1a = 0.0, slb1b = 0.0, slm2 = 0.0, slm1a = 0.0, slm1b = 0.0;
+    double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
       const uint2 r = p.rec[s];
       const uint32_t k = r.x, a = r.y;
       count += p.flags ? ((p.flags[s] >> 1) & 1) : 1;
       nall += k != 0;
-      if (k != 0 && k != last) { atomicAdd(h2 + k, 1u); ++N2; slb2 += lb2[k]; }
+      if (k != 0 && k != last) { atomicAdd(h2 + k, 1u); ++N2; }
       const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
-      if (fa) { atomicAdd(h1a + fa, 1u); ++N1a; slb1a += lb1a[fa]; }
-      if (fb) { atomicAdd(h1b + fb, 1u); ++N1b; slb1b += lb1b[fb]; }
+      if (fa) { atomicAdd(h1a + fa, 1u); ++N1a; }
+      if (fb) { atomicAdd(h1b + fb, 1u); ++N1b; }
     }
     __syncthreads();
+    // second walk: the first thread to reach a bin takes its whole count x (atomicExch clears it) and adds x (ln x - ln b)
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
       const uint2 r = p.rec[s];
       const uint32_t k = r.x, a = r.y;
-      if (k != 0 && k != last) slm2 += ln_mult(p, __ldcg(h2 + k));
+      if (k != 0 && k != last) {
+        const uint32_t x = atomicExch(h2 + k, 0u);
+        if (x) a2 = fma((double)x, ln_mult(p, x) - lb2[k], a2);
+      }
       const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
-      if (fa) slm1a += ln_mult(p, __ldcg(h1a + fa));
-      if (fb) slm1b += ln_mult(p, __ldcg(h1b + fb));
-    }
-    __syncthreads();
-    for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint2 r = p.rec[s];
-      const uint32_t k = r.x, a = r.y;
-      if (k != 0 && k != last) h2[k] = 0;
-      const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
-      if (fa) h1a[fa] = 0;
-      if (fb) h1b[fb] = 0;
+      if (fa) {
+        const uint32_t x = atomicExch(h1a + fa, 0u);
+        if (x) a1a = fma((double)x, ln_mult(p, x) - lb1a[fa], a1a);
+      }
+      if (fb) {
+        const uint32_t x = atomicExch(h1b + fb, 0u);
+        if (x) a1b = fma((double)x, ln_mult(p, x) - lb1b[fb], a1b);
+      }
     }
     // block reduce
-    double dv[6] = {slb2, slb1a, slb1b, slm2, slm1a, slm1b};
+    double dv[3] = {a2, a1a, a1b};
     int iv[5] = {N2, N1a, N1b, nall, count};
-    for (int q = 0; q < 6; ++q) { dv[q] = warp_sum(dv[q]); if (lane == 0) red_d[q][warp] = dv[q]; }
+    for (int q = 0; q < 3; ++q) { dv[q] = warp_sum(dv[q]); if (lane == 0) red_d[q][warp] = dv[q]; }
     for (int q = 0; q < 5; ++q) { iv[q] = warp_sum(iv[q]); if (lane == 0) red_i[q][warp] = iv[q]; }
     __syncthreads();
     if (tid == 0) {
-      for (int q = 0; q < 6; ++q) { double t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_d[q][x]; dv[q] = t; }
+      for (int q = 0; q < 3; ++q) { double t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_d[q][x]; dv[q] = t; }
       for (int q = 0; q < 5; ++q) { int t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_i[q][x]; iv[q] = t; }
-      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[3] - dv[0], dv[4] - dv[1], dv[5] - dv[2], p.B + g * 6);
+      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[0], dv[1], dv[2], p.B + g * 6);
     }
     __syncthreads();
   }
@@ -946,6 +950,28 @@ __global__ void __launch_bounds__(256) k_likelihood(const long long* x, const do
     for (int i = 0; i < 8; ++i) t += sd[i];
     *out = 2.0 * t;
     *flag = 0;
+  }
+}
+
+// legacy Poisson composite score (reference calculate_p :249-289): sum over bins with non-zero expectation of
+// poisson.logpmf(x, mu) = x ln mu - mu - lgamma(x + 1)
+__global__ void __launch_bounds__(256) k_poisson(const long long* x, const double* mu, long long n, double* out) {
+  __shared__ double sd[8];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double m = mu[i];
+    if (m != 0.0) {
+      const double xi = (double)x[i];
+      acc += (xi == 0.0 ? 0.0 : xi * log(m)) - m - lgamma(xi + 1.0);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += sd[i];
+    *out = t;
   }
 }
 

@@ -1,0 +1,166 @@
+"""Drop-in replacement for the function API of scripts/sims_scan.py (uricchio/2DSFS-scan), backed by CUDA kernels for B200.
+
+Same function names, parameter order and return shapes as the reference's free functions (reference lines 18-690).
+The twins differ from the class on purpose, and so do these: no None guards (an empty window raises
+ZeroDivisionError, :348/:415), T2D_diff with a MINUS sign (:497), window_end = start + W (:504), the 1D backgrounds
+of likelihood_scan left unfolded (:616-617).  All numerics run on the GPU through libtdsfs.so; no CPU fallback.
+"""
+from __future__ import annotations
+
+import csv
+import glob
+import os
+
+import numpy as np
+
+import tdsfs_capi as T
+from tdsfs_engine import (Engine, SnpTable, dense2d_to_dict, dict_to_dense2d, dict_to_folded1d, filter_flags, stat_lists,
+                          window_keys)
+from twoDSFS_class import parse_vcf_to_dict
+
+_engine = None
+
+
+def _eng():
+    global _engine
+    if _engine is None:
+        _engine = Engine(int(os.environ.get("TDSFS_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _engine
+
+
+def make_data_dict_vcf(vcf_filename, popinfo_filename):
+    """reference :18-120"""
+    return parse_vcf_to_dict(vcf_filename, popinfo_filename)
+
+
+def calculate_2d_sfs(data_dict, pop1, pop2, pop1_size, pop2_size, start_position, end_position, variant_type, fold=True):
+    """reference :123-234"""
+    table = SnpTable.from_dict(data_dict, pop1, pop2)
+    h2, _, _ = _eng().spectra(table, pop1_size, pop2_size, fold, filter_flags(table, start_position, end_position, variant_type))
+    return dense2d_to_dict(h2.astype(np.int64))
+
+
+def normalize_2d_sfs(sfs):
+    counts = list(sfs.values())
+    total = sum(counts[1:-1])
+    return {coords: values / total for coords, values in sfs.items()}
+
+
+def count_snps(window_data, variant_type):
+    return sum(1 for v in window_data.values() if variant_type is None or v.get("annotation") == variant_type)
+
+
+def calculate_1d_sfs(data_dict, pop, pop_size, start_position, end_position, variant_type):
+    """reference :262-302"""
+    table = SnpTable.from_dict(data_dict, pop, pop)
+    _, s1, _ = _eng().spectra(table, pop_size, pop_size, False, filter_flags(table, start_position, end_position, variant_type))
+    return {i: int(v) for i, v in enumerate(s1.tolist())}
+
+
+def fold_1d_sfs(sfs_dict):
+    num_chromosomes = max(sfs_dict.keys())
+    folded = {}
+    for freq, count in sfs_dict.items():
+        m = min(freq, num_chromosomes - freq)
+        folded[m] = folded[m] + count if m in folded else count
+    return folded
+
+
+def calculate_likelihood_1D(foreground_sfs, background_sfs):
+    """reference :325-395 (no guards: ZeroDivisionError on an empty spectrum)"""
+    return _eng().likelihood(foreground_sfs, background_sfs, guarded=False)
+
+
+def calculate_likelihood_2D(foreground_2d_sfs, background_2d_sfs):
+    """reference :398-440"""
+    return _eng().likelihood(foreground_2d_sfs, background_2d_sfs, guarded=False)
+
+
+def get_gens(main_dir):
+    search_strings = set()
+    for root, dirs, files in os.walk(main_dir):
+        for file in files:
+            parts = file.split('.')
+            if len(parts) == 5:
+                search_strings.add(parts[1])
+    return search_strings
+
+
+def process_window(data_dict, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_size, pop1, pop2, pop1_size, pop2_size, start_position,
+                   end_position, variant_type):
+    """reference :451-590: fixed-bp scan of one replicate against precomputed backgrounds."""
+    table = SnpTable.from_dict(data_dict, pop1, pop2)
+    if table.n == 0:
+        return {}
+    eng = _eng()
+    b2 = dict_to_dense2d(bg_2d_sfs, pop1_size, pop2_size)
+    b1a = dict_to_folded1d(bg_p1_sfs, pop1_size)
+    b1b = dict_to_folded1d(bg_p2_sfs, pop2_size)
+    eng.load(table, pop1_size, pop2_size, True, filter_flags(table, start_position, end_position, variant_type))
+    eng.background(T.BG_NONE)
+    eng.h.set_background(b2, b1a, b1b)
+    res = eng.scan(window_size, False)
+    live = (res["flags"] & T.F_EMPTY) == 0
+    keys = window_keys(table, res, live)
+    counts = res["snp_count"][live].tolist()
+    starts = res["start"][live].tolist()
+    T2, Ta, Tb = stat_lists(res, live)
+    results = {}
+    for k, c, st, T2D, T1, T2_ in zip(keys, counts, starts, T2, Ta, Tb):
+        if T2D is None or T1 is None or T2_ is None:
+            raise ZeroDivisionError("division by zero")  # count / total_fg with an empty spectrum (:415, :348)
+        results[k] = {"window_type": "background" if 0 <= st < 500000 else "foreground", "window_start": st,
+                      "window_end": st + window_size, "snp_count": c, "T2D": T2D, "T1D_p1": T1, "T1D_p2": T2_,
+                      "new_term_p1": T2D - T1, "new_term_p2": T2D - T2_, "T2D_diff": T2D - (T1 - T2_) / 2}
+    return results
+
+
+POPMAP_SIMS = "/Users/marlonalejandrocalderonbalcazar/Desktop/ECB/simulations/results/popmap_sims_copy.txt"
+
+
+def _iter_replicates(main_dir, popinfo_filename):
+    for generation in get_gens(main_dir):
+        target_vcfs = glob.glob(f"{main_dir}/iter*/*{generation}*.vcf.gz")
+        concatenated_vcfs = glob.glob(f"{main_dir}/concatenated_vcfs/gen.{generation}.concatenated.vcf.gz")
+        for vcf in concatenated_vcfs:
+            data_dict = make_data_dict_vcf(vcf, popinfo_filename)
+            bg_2d_sfs = calculate_2d_sfs(data_dict, 'p1', 'p2', 5, 5, start_position=0, end_position=500000, variant_type=None)
+            bg_p1_sfs = calculate_1d_sfs(data_dict, 'p1', 5, start_position=0, end_position=500000, variant_type=None)
+            bg_p2_sfs = calculate_1d_sfs(data_dict, 'p2', 5, start_position=0, end_position=500000, variant_type=None)
+            for vcf_input in target_vcfs:
+                data_dict_target = make_data_dict_vcf(vcf_input, popinfo_filename)
+                results = process_window(data_dict_target, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, 500000, 'p1', 'p2', 5, 5,
+                                         start_position=None, end_position=None, variant_type=None)
+                yield generation, int(vcf_input.split('.')[2]), results
+
+
+def likelihood_scan(main_dir, popinfo_filename=None):
+    """reference :646-690 (the definition that is live at import; it shadows the CSV-writing one at :593).
+    popinfo_filename: the reference hard-codes a path on the author's machine; pass yours here."""
+    popinfo_filename = popinfo_filename or POPMAP_SIMS
+    likelihood_results = {}
+    for generation, iteration_number, results in _iter_replicates(main_dir, popinfo_filename):
+        for key, value in results.items():
+            window_start, window_end = map(int, key.split(' ')[1].split('-'))
+            region = 'background' if window_end <= 1000000 else 'foreground'
+            likelihood_results[(generation, iteration_number, key)] = {'generation': generation, 'iteration': iteration_number,
+                                                                        'region': region, 'window_coords': key, 'likelihood': value}
+    return likelihood_results
+
+
+def likelihood_scan_to_csv(main_dir, output, popinfo_filename=None):
+    """The shadowed first definition of likelihood_scan (reference :593-644): one CSV row per window."""
+    popinfo_filename = popinfo_filename or POPMAP_SIMS
+    cols = ['generation', 'iteration', 'region', 'window_coords', 'snp_count', 'T2D', 'T1D_p1', 'T1D_p2', 'new_term_p1',
+            'new_term_p2', 'T2D_diff']
+    with open(output, 'w', newline='') as csvfile:
+        writer = csv.DictWriter(csvfile, fieldnames=cols)
+        writer.writeheader()
+        for generation, iteration_number, results in _iter_replicates(main_dir, popinfo_filename):
+            for window_coords, result in results.items():
+                window_start, window_end = window_coords.split(' ')[1].split('-')
+                region = 'background' if int(window_end) <= 1000000 else 'foreground'
+                writer.writerow({'generation': generation, 'iteration': iteration_number, 'region': region,
+                                 'window_coords': window_coords, 'snp_count': result["snp_count"], 'T2D': result["T2D"],
+                                 'T1D_p1': result["T1D_p1"], 'T1D_p2': result["T1D_p2"], 'new_term_p1': result["new_term_p1"],
+                                 'new_term_p2': result["new_term_p2"], 'T2D_diff': result["T2D_diff"]})

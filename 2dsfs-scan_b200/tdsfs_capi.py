@@ -20,6 +20,7 @@ EXPORTS = [
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
+    "tdsfs_poisson_score",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_version",
 ]
 
@@ -231,6 +232,13 @@ class Handle:
         T, flag = C.c_double(), C.c_int32()
         self._check(self._L.tdsfs_likelihood(self._h, _ptr(x), _ptr(b), C.c_int64(x.size), C.c_double(B), C.byref(T), C.byref(flag)))
         return T.value, bool(flag.value)
+
+    def poisson_score(self, x, mu):
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        out = C.c_double()
+        self._check(self._L.tdsfs_poisson_score(self._h, _ptr(x), _ptr(mu), C.c_int64(x.size), C.byref(out)))
+        return out.value
 
     # ---- synthetic + instrumentation
     def synth_genotypes(self, G_dev_ptr, S, snp0, words1, words2, ns1, ns2, seed, missing_rate=0.02, fst=0.05):

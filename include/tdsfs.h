@@ -104,8 +104,10 @@ int tdsfs_set_panel(tdsfs_t* ctx, int32_t n1, int32_t n2, int32_t fold);
 int tdsfs_load_counts(tdsfs_t* ctx, const uint16_t* cnt, int64_t S, const int32_t* pos, const int64_t* chrom_off,
                       int32_t C, const uint8_t* snp_flags);
 
-/* Genotype-level entry: 2-bit-per-call matrix G[S][words1+words2] of uint32 words, 16 calls per word
- * (call i of a word in bits 2i..2i+1), pop1 block then pop2 block, zero padded.
+/* Genotype-level entry: 2-bit-per-call matrix.  Per SNP: RW = words1 + words2 uint32 words of 16 calls each
+ * (call i of a word in bits 2i..2i+1), pop1 words then pop2 words, each population zero padded to a whole word.
+ * Memory layout "B32" (block transposed): SNPs in blocks of 32; word w of SNP s at uint32 index
+ * ((s / 32) * RW + w) * 32 + s % 32; the buffer holds ceil(S / 32) whole blocks (rows beyond S zero).
  * Codes: 0 = 0/0, 1 = 0/1, 3 = 1/1, 2 = missing.  ns1/ns2 = number of sample columns in each block.
  * Replaces the per-sample counting loop of make_data_dict_vcf (:118-130).  Host G is uploaded in chunks
  * asynchronously; the upload overlaps the count kernel of tdsfs_background. */
@@ -163,6 +165,10 @@ int tdsfs_window_spectra(tdsfs_t* ctx, int64_t window, uint64_t* sfs2d, uint64_t
  * b[n] background values, B = sum of b as the caller's language sums it.  *flag = 1 when the reference returns
  * None (sum x == 0 or B == 0). */
 int tdsfs_likelihood(tdsfs_t* ctx, const int64_t* x, const double* b, int64_t n, double B, double* T, int32_t* flag);
+
+/* Legacy Poisson composite score, calculate_p (:249-289, twoDSFS.py:336-374): sum over bins with mu != 0 of
+ * poisson.logpmf(x, mu), mu = S_w * p_bg. */
+int tdsfs_poisson_score(tdsfs_t* ctx, const int64_t* x, const double* mu, int64_t n, double* score);
 
 /* ---- synthetic input (benchmark configs of BASELINE.json) + instrumentation ---------------------------------- */
 /* Fill a DEVICE genotype matrix with the synthetic panel of SURVEY.md 8(d): per-SNP ancestral frequency

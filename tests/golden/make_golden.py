@@ -284,7 +284,20 @@ def do_small():
         st2, rs = call(sims["calculate_likelihood_1D"], fg, bg)
         lk.append(dict(fg=list(fg.values()), bg=list(bg.values()), cls_status=st, cls=(jf(r) if st == "ok" else r),
                        sims_status=st2, sims=(jf(rs) if st2 == "ok" else rs)))
-    json.dump(dict(cases=cases, likelihood=lk), open(f"{HERE}/small_cases.json", "w"), allow_nan=True)
+    # legacy Poisson score KATs (calculate_p, class :249-289)
+    pk = []
+    for t in range(12):
+        nb = int(r2.integers(4, 40))
+        fgp = {(i // 5, i % 5): int(v) for i, v in enumerate(r2.poisson(r2.choice([0.5, 4.0, 30.0]), nb))}
+        bgp = {k: float(v) for k, v in zip(fgp, r2.random(nb))}
+        for k in list(bgp)[:: 7]:
+            bgp[k] = 0.0  # zero expectation bins are skipped (:282-283)
+        tot = sum(bgp.values())
+        bgp = {k: v / tot for k, v in bgp.items()}
+        st, r = call(inst.calculate_p, fgp, bgp)
+        assert st == "ok"
+        pk.append(dict(fg=[[k[0], k[1], v] for k, v in fgp.items()], bg=[[k[0], k[1], v] for k, v in bgp.items()], value=jf(r)))
+    json.dump(dict(cases=cases, likelihood=lk, poisson=pk), open(f"{HERE}/small_cases.json", "w"), allow_nan=True)
     print("small done")
 
 
