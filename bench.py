@@ -244,6 +244,8 @@ def run_b200(args, cfg):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n1, n2, W = cfg["n1"], cfg["n2"], cfg["W"]
     w1, w2 = words_for(n1), words_for(n2)
