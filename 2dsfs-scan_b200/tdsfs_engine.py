@@ -102,6 +102,10 @@ class Engine:
         if self._panel != (n1, n2, bool(fold)):
             self.h.set_panel(n1, n2, fold)
             self._panel = (n1, n2, bool(fold))
+        if getattr(table, "G", None) is not None and cnt is None:  # PackedPanel: genotype-level entry (K1 from 2-bit calls)
+            self.h.load_genotypes(table.G, table.n, table.W1, table.W2, table.ns1, table.ns2,
+                                  np.ascontiguousarray(table.pos, dtype=np.int32), table.off, fixups=table.fixups, flags=flags)
+            return
         c = table.cnt if cnt is None else cnt
         self.h.load_counts(np.ascontiguousarray(c, dtype=np.uint16), np.ascontiguousarray(table.pos, dtype=np.int32), table.off, flags)
 

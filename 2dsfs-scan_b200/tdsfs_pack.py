@@ -46,3 +46,116 @@ def pack_codes(codes1: np.ndarray, codes2: np.ndarray):
     """codes[S, ns] of 2-bit codes -> (G in B32 layout (flat uint32), W1, W2)."""
     b1, b2 = _pack_block(np.asarray(codes1)), _pack_block(np.asarray(codes2))
     return to_b32(np.concatenate([b1, b2], axis=1)), b1.shape[1], b2.shape[1]
+
+
+# ----------------------------------------------------------------------------------------------- VCF packer (K0, C++)
+import ctypes as _C
+import os as _os
+
+_PACK_LIB = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "lib", "libtdsfs_pack.so")
+_plib = None
+
+
+def _packer():
+    global _plib
+    if _plib is None:
+        if not _os.path.exists(_PACK_LIB):
+            raise RuntimeError(f"{_PACK_LIB} not found: build it with `python 2dsfs-scan_b200/build.py`")
+        L = _C.CDLL(_PACK_LIB)
+        L.tdsfs_pack_vcf.restype = _C.c_void_p
+        L.tdsfs_pack_vcf.argtypes = [_C.c_char_p, _C.c_char_p, _C.c_char_p, _C.c_char_p, _C.c_int]
+        L.tdsfs_pack_last_error.restype = _C.c_char_p
+        for f in ("tdsfs_pack_genotypes", "tdsfs_pack_positions", "tdsfs_pack_chrom_off", "tdsfs_pack_ann_codes", "tdsfs_pack_fixups"):
+            getattr(L, f).restype = _C.c_void_p
+            getattr(L, f).argtypes = [_C.c_void_p]
+        for f in ("tdsfs_pack_chrom_names", "tdsfs_pack_ann_vocab"):
+            getattr(L, f).restype = _C.c_char_p
+            getattr(L, f).argtypes = [_C.c_void_p]
+        L.tdsfs_pack_dims.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.tdsfs_pack_free.argtypes = [_C.c_void_p]
+        _plib = L
+    return _plib
+
+
+class PackedPanel:
+    """A VCF packed for the GPU: the array form of a data_dict restricted to two populations, at genotype level.
+    Accepted by the scanners of LikelihoodInference_jointSFS in place of a data_dict (fast path: no Python dict)."""
+
+    def __init__(self):
+        self.G = None            # uint32, B32 layout
+        self.W1 = self.W2 = self.ns1 = self.ns2 = 0
+        self.pos = None          # int64 (int32 range), sorted by (chromosome string, position)
+        self.off = None
+        self.chroms = []
+        self.ann = None          # object array of annotation strings
+        self.fixups = None
+        self.pops = (None, None)
+        self.n = 0
+        self.last_key_row = -1
+        self.n_records = self.n_skipped = 0
+
+    def __len__(self):
+        return self.n
+
+    def check_ranges(self):
+        pass
+
+    def counts(self):
+        """(ref1, alt1, ref2, alt2) per SNP decoded on the host (debug / tests only)."""
+        rows = from_b32(self.G, self.n, self.W1 + self.W2)
+        out = np.zeros((self.n, 4), dtype=np.int64)
+        for p, (w0, w1, ns) in enumerate(((0, self.W1, self.ns1), (self.W1, self.W1 + self.W2, self.ns2))):
+            blk = rows[:, w0:w1]
+            codes = np.stack([(blk >> np.uint32(2 * i)) & np.uint32(3) for i in range(16)], axis=-1).reshape(self.n, -1)[:, :ns]
+            alt = (codes == CODE_HET).sum(1) + 2 * (codes == CODE_HOMALT).sum(1)
+            out[:, 2 * p + 1] = alt
+            out[:, 2 * p] = (codes == CODE_HET).sum(1) + 2 * (codes == CODE_HOMREF).sum(1)
+        if self.fixups is not None:
+            for f in self.fixups:
+                out[f["snp"], 2 * f["pop"]] += f["dref"]
+                out[f["snp"], 2 * f["pop"] + 1] += f["dalt"]
+        return out
+
+
+def pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, nthreads=0):
+    """gzip VCF + popmap -> PackedPanel with the reference's ingest rules (make_data_dict_vcf, reference :36-138)."""
+    L = _packer()
+    h = L.tdsfs_pack_vcf(str(vcf_filename).encode(), str(popinfo_filename).encode(), str(pop1).encode(), str(pop2).encode(), int(nthreads))
+    if not h:
+        msg = L.tdsfs_pack_last_error().decode()
+        if "cannot open" in msg:
+            raise FileNotFoundError(msg)
+        if "not in list" in msg or "invalid literal" in msg:
+            raise ValueError(msg)
+        if "index out of range" in msg:
+            raise IndexError(msg)
+        raise RuntimeError(msg)
+    try:
+        dims = (_C.c_int64 * 8)()
+        dims2 = (_C.c_int64 * 4)()
+        L.tdsfs_pack_dims(h, dims, dims2)
+        S, W1, W2, ns1, ns2, C, nfix, last = [int(v) for v in dims]
+        P = PackedPanel()
+        P.n, P.W1, P.W2, P.ns1, P.ns2, P.last_key_row = S, W1, W2, ns1, ns2, last
+        P.n_records, P.n_skipped = int(dims2[0]), int(dims2[1])
+        gw = int(dims2[3])
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(_C.cast(ptr, _C.POINTER(_C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+
+        P.G = arr(L.tdsfs_pack_genotypes(h), gw, np.uint32)
+        P.pos = arr(L.tdsfs_pack_positions(h), S, np.int32).astype(np.int64)
+        P.off = arr(L.tdsfs_pack_chrom_off(h), C + 1, np.int64)
+        names = L.tdsfs_pack_chrom_names(h).decode()
+        P.chroms = names.split("\n")[:-1] if names else []
+        vocab = L.tdsfs_pack_ann_vocab(h).decode().split("\n")[:-1]
+        codes = arr(L.tdsfs_pack_ann_codes(h), S, np.int32)
+        P.ann = np.array(vocab, dtype=object)[codes] if S else np.array([], dtype=object)
+        fix_dt = np.dtype([("snp", "<i8"), ("pop", "<i4"), ("dref", "<i4"), ("dalt", "<i4")], align=True)
+        P.fixups = arr(L.tdsfs_pack_fixups(h), nfix, fix_dt) if nfix else None
+        P.pops = (pop1, pop2)
+        return P
+    finally:
+        L.tdsfs_pack_free(h)

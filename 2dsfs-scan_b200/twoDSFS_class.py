@@ -18,6 +18,7 @@ import os
 import numpy as np
 
 import tdsfs_capi as T
+from tdsfs_pack import PackedPanel, pack_vcf
 from tdsfs_engine import (Engine, SnpTable, dense2d_to_dict, dict_to_dense2d, dict_to_folded1d, filter_flags, stat_lists,
                           window_keys)
 
@@ -93,6 +94,10 @@ class LikelihoodInference_jointSFS:
     def _table(self, data_dict, pop1=None, pop2=None):
         pop1 = self.pop1 if pop1 is None else pop1
         pop2 = self.pop2 if pop2 is None else pop2
+        if isinstance(data_dict, PackedPanel):  # fast path: a VCF packed by make_packed_panel / tdsfs_pack.pack_vcf
+            if (pop1, pop2) != tuple(data_dict.pops):
+                raise TypeError(f"this PackedPanel holds populations {data_dict.pops}; {(pop1, pop2)} requested (use a data_dict)")
+            return data_dict
         n = len(data_dict)
         tag = (id(data_dict), n, pop1, pop2, next(iter(data_dict)) if n else None, next(reversed(data_dict)) if n else None)
         if self._tcache is None or self._tcache[0] != tag:
@@ -117,6 +122,12 @@ class LikelihoodInference_jointSFS:
     # ------------------------------------------------------------------ ingest
     def make_data_dict_vcf(self, vcf_filename, popinfo_filename):
         return parse_vcf_to_dict(vcf_filename, popinfo_filename)
+
+    def make_packed_panel(self, vcf_filename=None, popinfo_filename=None, nthreads=0):
+        """Fast ingest (not in the reference): the same VCF + popmap rules as make_data_dict_vcf, packed by the C++ host
+        packer into the 2-bit genotype matrix the GPU consumes.  The result can be passed to combined_scan, scan_chooseChr,
+        scan_precomputed_BG, scan_*_bySNPs and calculate_2d_sfs wherever they take a data_dict."""
+        return pack_vcf(vcf_filename or self.vcf_filename, popinfo_filename or self.popinfo_filename, self.pop1, self.pop2, nthreads)
 
     # ------------------------------------------------------------------ spectra
     def calculate_2d_sfs(self, data_dict):
@@ -172,6 +183,14 @@ class LikelihoodInference_jointSFS:
         self.start_position = start_position
         self.end_position = end_position
         self.variant_type = variant_type
+        if isinstance(data_dict, PackedPanel):
+            if pop not in data_dict.pops:
+                raise TypeError(f"this PackedPanel holds populations {data_dict.pops}")
+            first = pop == data_dict.pops[0]
+            n1, n2 = (pop_size, self.pop2_size) if first else (self.pop1_size, pop_size)
+            flags = filter_flags(data_dict, start_position, end_position, variant_type)
+            _, s1a, s1b = self._eng().spectra(data_dict, n1, n2, False, flags)
+            return {i: int(v) for i, v in enumerate((s1a if first else s1b).tolist())}
         table = self._table(data_dict, pop, pop)
         flags = filter_flags(table, start_position, end_position, variant_type)
         _, s1, _ = self._eng().spectra(table, pop_size, pop_size, False, flags)
@@ -291,6 +310,8 @@ class LikelihoodInference_jointSFS:
         self.background_2d_sfs = background_2d_sfs
         self.window_size = window_size
         table = self._table(data_dict)
+        if isinstance(table, PackedPanel):
+            raise TypeError("T2D_scan needs a data_dict (its insertion-order quirk is not defined for a packed panel)")
         if table.n == 0:
             return {}
         self._int_filters()
@@ -401,6 +422,8 @@ class LikelihoodInference_jointSFS:
         self._int_filters()
         # normalised backgrounds (:1334-1336): ZeroDivisionError when the chromosome has no interior SNP, as the reference
         c = table.chroms.index(background_chromosome)
+        if isinstance(table, PackedPanel):
+            raise TypeError("scan_chooseChr_bySNPs needs a data_dict (use scan_chooseChr / scan_perChr_bySNPs with a packed panel)")
         sub = SnpTable()
         lo, hi = int(table.off[c]), int(table.off[c + 1])
         sub.chroms, sub.off, sub.pos, sub.cnt, sub.ann, sub.keys, sub.pops, sub.n, sub.last_key_row = (
@@ -442,6 +465,8 @@ class LikelihoodInference_jointSFS:
         self.data_dict = data_dict
         self.window_size = window_size
         table = self._table(data_dict)
+        if isinstance(table, PackedPanel):
+            raise TypeError("sims_process_window needs a data_dict")
         if table.n == 0:
             return {}
         self._int_filters()

@@ -169,3 +169,36 @@ def test_ecb_subset_vcf_end_to_end(mods):
     compare_result_lists(inst.combined_scan(d, 20000), exp["combined_20kb"]["result"], "20kb")
     compare_result_lists(inst.combined_scan(d, 500000), exp["combined_500kb"]["result"], "500kb")
     compare_result_lists(inst.scan_perChr_bySNPs(d, 500), exp["bysnps_500"]["result"], "500snps")
+
+
+def test_packed_panel_fast_path_equals_dict_path(mods):
+    """K0 (C++ packer) -> genotype-level GPU entry gives the same scans as the dict path on the same VCF."""
+    K, _ = mods
+    vcf, pm = os.path.join(GOLDEN, "ecb_subset.vcf.gz"), os.path.join(GOLDEN, "ecb_subset.popmap.txt")
+    inst = K.LikelihoodInference_jointSFS(vcf, pm)
+    d = inst.make_data_dict_vcf(vcf, pm)
+    P = inst.make_packed_panel()
+    assert len(P) == len(d)
+
+    def same(a, b):
+        assert list(a) == list(b)
+        for k in a:
+            for f in a[k]:
+                assert close(a[k][f], b[k][f], 1e-11), (k, f, a[k][f], b[k][f])
+
+    same(inst.combined_scan(P, 20000), inst.combined_scan(d, 20000))
+    same(inst.scan_perChr_bySNPs(P, 500), inst.scan_perChr_bySNPs(d, 500))
+    same(inst.scan_chooseChr(P, 500000, "NC_087088.1"), inst.scan_chooseChr(d, 500000, "NC_087088.1"))
+    assert inst.calculate_2d_sfs(P) == inst.calculate_2d_sfs(d)
+    assert inst.calculate_1d_sfs(P, "bv", 14, None, None, None) == inst.calculate_1d_sfs(d, "bv", 14, None, None, None)
+    bg2 = inst.calculate_2d_sfs(d)
+    b1 = inst.fold_1d_sfs(inst.calculate_1d_sfs(d, "uv", 18, None, None, None))
+    b2 = inst.fold_1d_sfs(inst.calculate_1d_sfs(d, "bv", 14, None, None, None))
+    same(inst.scan_precomputed_BG(P, 500000, bg2, b1, b2), inst.scan_precomputed_BG(d, 500000, bg2, b1, b2))
+    # the hand-built ingest fixture has half calls / haploid calls: fix-ups travel with the packed panel
+    vcf, pm = os.path.join(GOLDEN, "ingest_small.vcf.gz"), os.path.join(GOLDEN, "ingest_small.popmap.txt")
+    inst = K.LikelihoodInference_jointSFS(vcf, pm, pop1_size=3, pop2_size=3)
+    d, P = inst.make_data_dict_vcf(vcf, pm), inst.make_packed_panel()
+    assert P.fixups is not None and len(P.fixups) > 0
+    assert inst.calculate_2d_sfs(P) == inst.calculate_2d_sfs(d)
+    assert inst.calculate_1d_sfs(P, "uv", 3, None, None, None) == inst.calculate_1d_sfs(d, "uv", 3, None, None, None)
