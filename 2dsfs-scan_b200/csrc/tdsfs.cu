@@ -89,7 +89,7 @@ struct tdsfs_ctx {
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
   bool float_bg = false, tables_ready = false, fin_timed = false;
-  int score_group_warps = 2;  // warps per window in the shared-memory scorer (1, 2 or 4)
+  int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
   int* d_err = nullptr;
   // windows / results
   long long ncand = 0, cand_cap = 0;

@@ -192,6 +192,41 @@ __device__ __forceinline__ void count_block_b32(const uint32_t* blk, int Wrt, ui
   M = pc.miss.total();
 }
 
+// Both population blocks of one SNP at once (same word count): four independent carry-save chains (bits/missing x 2
+// populations) instead of two -- the count kernel is bound by dependent LOP3 latency with ~3 warps per scheduler.
+template <int TW>
+__device__ __forceinline__ void count_two_blocks_b32(const uint32_t* blk1, const uint32_t* blk2, uint32_t& T1, uint32_t& M1,
+                                                     uint32_t& T2, uint32_t& M2) {
+  PopCounts p1, p2;
+  int w = 0;
+#pragma unroll
+  for (; w + 8 <= TW; w += 8) {
+    const uint32_t* q1 = blk1 + w * BLK;
+    const uint32_t* q2 = blk2 + w * BLK;
+    uint4 a1 = make_uint4(q1[0], q1[BLK], q1[2 * BLK], q1[3 * BLK]);
+    uint4 a2 = make_uint4(q2[0], q2[BLK], q2[2 * BLK], q2[3 * BLK]);
+    uint4 b1 = make_uint4(q1[4 * BLK], q1[5 * BLK], q1[6 * BLK], q1[7 * BLK]);
+    uint4 b2 = make_uint4(q2[4 * BLK], q2[5 * BLK], q2[6 * BLK], q2[7 * BLK]);
+    p1.chunk8(a1, b1);
+    p2.chunk8(a2, b2);
+  }
+  if (w + 4 <= TW) {
+    const uint32_t* q1 = blk1 + w * BLK;
+    const uint32_t* q2 = blk2 + w * BLK;
+    p1.chunk4(q1[0], q1[BLK], q1[2 * BLK], q1[3 * BLK]);
+    p2.chunk4(q2[0], q2[BLK], q2[2 * BLK], q2[3 * BLK]);
+    w += 4;
+  }
+  if (w < TW) {
+    const uint32_t* q1 = blk1 + w * BLK;
+    const uint32_t* q2 = blk2 + w * BLK;
+    p1.chunk4(q1[0], (w + 1 < TW) ? q1[BLK] : 0u, (w + 2 < TW) ? q1[2 * BLK] : 0u, 0u);
+    p2.chunk4(q2[0], (w + 1 < TW) ? q2[BLK] : 0u, (w + 2 < TW) ? q2[2 * BLK] : 0u, 0u);
+  }
+  T1 = p1.bits.total(); M1 = p1.miss.total();
+  T2 = p2.bits.total(); M2 = p2.miss.total();
+}
+
 // ------------------------------------------------------------------------------------------------ row sink
 // Shared-memory privatised background histograms of ONE background group per CTA.
 struct SinkSmem {
@@ -378,8 +413,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
         if (s < p.r1) {
           const uint32_t* rowp = tile + (size_t)b * block_words + lane;
           uint32_t T1, M1, T2, M2;
-          count_block_b32<TW1>(rowp, W1, T1, M1);
-          count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
+          if (TW1 > 0 && TW1 == TW2) {
+            count_two_blocks_b32<TW1>(rowp, rowp + W1 * BLK, T1, M1, T2, M2);
+          } else {
+            count_block_b32<TW1>(rowp, W1, T1, M1);
+            count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
+          }
           const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
           const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
           sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
@@ -645,15 +684,15 @@ __device__ __forceinline__ void write_result(const ScoreParams& p, long long id,
 // table of the window's 2D bins (one word per slot: bin << 10 | multiplicity), the list of occupied slots, packed
 // 16-bit folded 1D histograms and a small reduction scratch.
 //   pass 1 (per SNP)          insert the 2D bin, bump the two folded 1D bins      (all records of a thread in flight)
-//   pass 2 (per distinct bin) acc += x (ln x - ln b); the slot is cleared on the way
+//   pass 2 (table walk)       acc += x (ln x - ln b) for every occupied slot, cleared on the way
 //   pass 3 (per 1D bin pair)  same for both 1D spectra, bins cleared on the way
 // Several warps per window keep the same shared-memory footprint per window but multiply the resident warps, which is
 // what hides the shared-atomic and gather latencies.
 constexpr int SCORE_WARPS = 8;
 constexpr int KEY_SHIFT = 10;  // multiplicity field (< 1024, WCAP = 768)
 __host__ __device__ inline int score_group_smem_words(int n1, int n2) {
-  // table | slot list | counter | 1D bins (padded to an even word count) | reduction scratch (4 warps x 10 words)
-  return HASH_SLOTS + WCAP / 2 + 2 + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + 4 * 10;
+  // table | 1D bins (padded to an even word count) | reduction scratch (4 warps x 10 words)
+  return HASH_SLOTS + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + 4 * 10;
 }
 // limits of the shared-memory scorer; panels beyond them are scored by the CTA kernel only
 __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
@@ -661,7 +700,7 @@ __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
 }
 
 __device__ __forceinline__ void acc_bin(double& acc, uint32_t x, const double* lnI, const double* lb, int k) {
-  if (x) acc = fma((double)x, __ldg(lnI + x) - __ldg(lb + k), acc);
+  if (x) acc = fma((double)x, __ldg(lnI + x) - __ldg(lb + k), acc);  // (branch-free: a divergent x == 1 path doubles the gathers)
 }
 
 template <int G>
@@ -673,9 +712,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   const int grp = warp / G, wg = warp % G, tg = wg * 32 + lane;
   const int gwords = score_group_smem_words(p.n1, p.n2);
   uint32_t* tab = sm32 + (size_t)grp * gwords;
-  uint16_t* slist = reinterpret_cast<uint16_t*>(tab + HASH_SLOTS);
-  uint32_t* nd = tab + HASH_SLOTS + WCAP / 2;  // number of occupied slots
-  uint32_t* h1a = nd + 2;                      // packed 16-bit bins: bin f in word f >> 1, half f & 1
+  uint32_t* h1a = tab + HASH_SLOTS;            // packed 16-bit bins: bin f in word f >> 1, half f & 1
   const int nw1 = (p.n1 + 2) / 2, nw2 = (p.n2 + 2) / 2;
   uint32_t* h1b = h1a + nw1;
   uint32_t* red = h1a + ((nw1 + nw2 + 1) & ~1);  // [4][10] (8-byte aligned): per warp {a2, a1a, a1b (doubles), N-pack, count, nall}
@@ -683,7 +720,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     if (G == 1) __syncwarp(); else named_bar_sync(1 + grp, GT);
   };
   for (int i = tg; i < HASH_SLOTS; i += GT) tab[i] = EMPTY_KEY;
-  for (int i = tg; i < 2 + nw1 + nw2; i += GT) nd[i] = 0;
+  for (int i = tg; i < nw1 + nw2; i += GT) h1a[i] = 0;
   gsync();
   const uint32_t last = (uint32_t)p.bins2d - 1;
   const bool has_flags = p.flags != nullptr;
@@ -718,11 +755,11 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
         if (p.snp_mode) nall += k != 0;
         if (k != 0 && k != last) {
           uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
-          while (true) {
+          while (true) {  // read first: a shared-memory CAS costs about twice a load or an add
             uint32_t e = tab[h];
             if (e == EMPTY_KEY) {
               e = atomicCAS(tab + h, EMPTY_KEY, (k << KEY_SHIFT) | 1u);
-              if (e == EMPTY_KEY) { slist[atomicAdd(nd, 1u)] = (uint16_t)h; break; }
+              if (e == EMPTY_KEY) break;
             }
             if ((e >> KEY_SHIFT) == k) { atomicAdd(tab + h, 1u); break; }
             h = (h + 1) & (HASH_SLOTS - 1);
@@ -734,22 +771,18 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
       }
     }
     gsync();
-    // ---- pass 2: distinct 2D bins, two per thread in flight
+    // ---- pass 2: walk the table (shared-memory atomics are the scarce resource here: no occupied-slot list is kept)
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     uint32_t N2 = 0, N1a = 0, N1b = 0;
-    const int ndist = (int)*nd;
-    for (int j = tg; j < ndist; j += 2 * GT) {
-      const bool two = j + GT < ndist;
-      const uint32_t s0 = slist[j], s1 = two ? slist[j + GT] : 0u;
-      const uint32_t e0 = tab[s0], e1 = two ? tab[s1] : 0u;
-      tab[s0] = EMPTY_KEY;
-      if (two) tab[s1] = EMPTY_KEY;
-      const uint32_t x0 = e0 & ((1u << KEY_SHIFT) - 1), x1 = e1 & ((1u << KEY_SHIFT) - 1);
-      const double l0 = __ldg(lb2 + (e0 >> KEY_SHIFT)), l1 = two ? __ldg(lb2 + (e1 >> KEY_SHIFT)) : 0.0;
-      const double m0 = __ldg(p.lnI + x0), m1 = __ldg(p.lnI + x1);
-      a2 = fma((double)x0, m0 - l0, a2);
-      if (two) a2 = fma((double)x1, m1 - l1, a2);
-      N2 += x0 + x1;
+#pragma unroll 2
+    for (int j = tg; j < HASH_SLOTS; j += GT) {
+      const uint32_t e = tab[j];
+      if (e != EMPTY_KEY) {
+        tab[j] = EMPTY_KEY;
+        const uint32_t x = e & ((1u << KEY_SHIFT) - 1);
+        acc_bin(a2, x, p.lnI, lb2, (int)(e >> KEY_SHIFT));
+        N2 += x;
+      }
     }
     // ---- pass 3: folded 1D bins (two per word)
     for (int w = tg; w < nw1; w += GT) {
@@ -808,7 +841,6 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
         p.r_flags[id] = f;
         p.r_T2[id] = Tq;
         p.r_n2[id] = Nq;
-        *nd = 0;
       } else if (lane == 1) {
         p.r_T1a[id] = Tq;
         p.r_n1a[id] = Nq;
