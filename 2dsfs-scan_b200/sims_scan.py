@@ -115,6 +115,45 @@ def process_window(data_dict, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_size, pop1
     return results
 
 
+def process_window_batch(data_dicts, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_size, pop1, pop2, pop1_size, pop2_size, start_position,
+                         end_position, variant_type):
+    """All replicates of one generation in ONE launch (BASELINE.json configs[2]): every replicate becomes a block of
+    pseudo-chromosomes, so the 2-3 windows x hundreds of replicates are scored by one pass of the count / boundary / score
+    kernels instead of one latency-bound round trip per replicate.  Returns [process_window(d, ...) for d in data_dicts]."""
+    tables = [SnpTable.from_dict(d, pop1, pop2) for d in data_dicts]
+    big = SnpTable()
+    big.chroms, offs, base = [], [0], 0
+    for r, t in enumerate(tables):
+        big.chroms += [(r, c) for c in t.chroms]
+        offs += (t.off[1:] + base).tolist()
+        base += t.n
+    big.off = np.asarray(offs, dtype=np.int64)
+    big.pos = np.concatenate([t.pos for t in tables]) if tables else np.zeros(0, np.int64)
+    big.cnt = np.concatenate([t.cnt for t in tables]) if tables else np.zeros((0, 4), np.int64)
+    big.ann = np.concatenate([t.ann for t in tables]) if tables else np.array([], dtype=object)
+    big.keys, big.pops, big.n, big.last_key_row = [], (pop1, pop2), base, -1
+    out = [{} for _ in tables]
+    if base == 0:
+        return out
+    eng = _eng()
+    eng.load(big, pop1_size, pop2_size, True, filter_flags(big, start_position, end_position, variant_type))
+    eng.background(T.BG_NONE)
+    eng.h.set_background(dict_to_dense2d(bg_2d_sfs, pop1_size, pop2_size), dict_to_folded1d(bg_p1_sfs, pop1_size),
+                         dict_to_folded1d(bg_p2_sfs, pop2_size))
+    res = eng.scan(window_size, False)
+    live = (res["flags"] & T.F_EMPTY) == 0
+    T2, Ta, Tb = stat_lists(res, live)
+    for ci, c, st, en, T2D, T1, T2_ in zip(res["chrom"][live].tolist(), res["snp_count"][live].tolist(), res["start"][live].tolist(),
+                                           res["end"][live].tolist(), T2, Ta, Tb):
+        if T2D is None or T1 is None or T2_ is None:
+            raise ZeroDivisionError("division by zero")
+        r, chrom = big.chroms[ci]
+        out[r][f"{chrom} {st}-{en}"] = {"window_type": "background" if 0 <= st < 500000 else "foreground", "window_start": st,
+                                        "window_end": st + window_size, "snp_count": c, "T2D": T2D, "T1D_p1": T1, "T1D_p2": T2_,
+                                        "new_term_p1": T2D - T1, "new_term_p2": T2D - T2_, "T2D_diff": T2D - (T1 - T2_) / 2}
+    return out
+
+
 POPMAP_SIMS = "/Users/marlonalejandrocalderonbalcazar/Desktop/ECB/simulations/results/popmap_sims_copy.txt"
 
 
@@ -127,10 +166,10 @@ def _iter_replicates(main_dir, popinfo_filename):
             bg_2d_sfs = calculate_2d_sfs(data_dict, 'p1', 'p2', 5, 5, start_position=0, end_position=500000, variant_type=None)
             bg_p1_sfs = calculate_1d_sfs(data_dict, 'p1', 5, start_position=0, end_position=500000, variant_type=None)
             bg_p2_sfs = calculate_1d_sfs(data_dict, 'p2', 5, start_position=0, end_position=500000, variant_type=None)
-            for vcf_input in target_vcfs:
-                data_dict_target = make_data_dict_vcf(vcf_input, popinfo_filename)
-                results = process_window(data_dict_target, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, 500000, 'p1', 'p2', 5, 5,
+            dicts = [make_data_dict_vcf(v, popinfo_filename) for v in target_vcfs]
+            batch = process_window_batch(dicts, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, 500000, 'p1', 'p2', 5, 5,
                                          start_position=None, end_position=None, variant_type=None)
+            for vcf_input, results in zip(target_vcfs, batch):
                 yield generation, int(vcf_input.split('.')[2]), results
 
 

@@ -202,3 +202,51 @@ def test_packed_panel_fast_path_equals_dict_path(mods):
     assert P.fixups is not None and len(P.fixups) > 0
     assert inst.calculate_2d_sfs(P) == inst.calculate_2d_sfs(d)
     assert inst.calculate_1d_sfs(P, "uv", 3, None, None, None) == inst.calculate_1d_sfs(d, "uv", 3, None, None, None)
+
+
+def _write_sim_vcf(path, rng, nsnp, L):
+    import gzip
+    samples = [f"i{k}" for k in range(10)]
+    pos = np.sort(rng.choice(np.arange(1, L), size=nsnp, replace=False))
+    with gzip.open(path, "wt") as f:
+        f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n")
+        for p in pos:
+            fr = min(max(rng.beta(0.4, 0.8), 0.02), 0.98)
+            gts = ["|".join(str(int(rng.random() < fr)) for _ in range(2)) for _ in samples]
+            f.write(f"1\t{p}\t.\tA\tG\t.\tPASS\t.\tGT\t" + "\t".join(gts) + "\n")
+
+
+def test_sims_directory_driver_batched(mods, tmp_path):
+    """likelihood_scan over a simulation directory (BASELINE configs[2]): per-generation backgrounds from the concatenated
+    VCF (1D left unfolded, region 0..500000), all replicates of a generation scored in one batched launch ==
+    the oracle's process_window per replicate."""
+    import sfs_oracle as O
+    K, S = mods
+    rng = np.random.default_rng(42)
+    main = tmp_path / "sims"
+    (main / "concatenated_vcfs").mkdir(parents=True)
+    pm = tmp_path / "popmap.txt"
+    pm.write_text("".join(f"i{k}\t{'p1' if k < 5 else 'p2'}\n" for k in range(10)))
+    gens = ["1000", "2000"]
+    for g in gens:
+        _write_sim_vcf(str(main / "concatenated_vcfs" / f"gen.{g}.concatenated.vcf.gz"), rng, 3000, 1500000)
+        for it in range(1, 4):
+            d = main / f"iter{it}"
+            d.mkdir(exist_ok=True)
+            _write_sim_vcf(str(d / f"sim.{g}.{it}.vcf.gz"), rng, 1500, 1500000)
+    assert S.get_gens(str(main)) == set(gens)
+    got = S.likelihood_scan(str(main), popinfo_filename=str(pm))
+    assert len(got) == 2 * 3 * 3
+    for (g, it, key), rec in got.items():
+        bgd = O.make_data_dict_vcf(str(main / "concatenated_vcfs" / f"gen.{g}.concatenated.vcf.gz"), str(pm))
+        b2 = O.calculate_2d_sfs(bgd, "p1", "p2", 5, 5, 0, 500000, None)
+        b1 = O.calculate_1d_sfs(bgd, "p1", 5, 0, 500000, None)
+        b1b = O.calculate_1d_sfs(bgd, "p2", 5, 0, 500000, None)
+        d = O.make_data_dict_vcf(str(main / f"iter{it}" / f"sim.{g}.{it}.vcf.gz"), str(pm))
+        exp = O.sims_process_window(d, b2, b1, b1b, 500000, "p1", "p2", 5, 5, None, None, None)
+        assert rec["region"] == ("background" if int(key.split("-")[1]) <= 1000000 else "foreground")
+        for f, v in exp[key].items():
+            assert close(rec["likelihood"][f], v), (g, it, key, f)
+    out = tmp_path / "sims.csv"
+    S.likelihood_scan_to_csv(str(main), str(out), popinfo_filename=str(pm))
+    assert len(out.read_text().splitlines()) == 1 + 18
