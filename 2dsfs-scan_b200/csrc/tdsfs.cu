@@ -97,6 +97,12 @@ struct tdsfs_ctx {
   long long cand_W = -1;
   int cand_snp = -1;
   int groups_mode = -1, groups_chrom = -1;  // what d_bg_group / d_score_group currently hold
+  // window plan launched ahead of the scan on a side stream (tdsfs_plan_bp / _snp)
+  cudaStream_t plan_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_plan0 = nullptr;
+  long long plan_W = -1;
+  int plan_snp = -1;
+  bool planned_last = false;
   long long* d_cand_off = nullptr;
   int32_t *d_wlo = nullptr, *d_whi = nullptr, *d_wchrom = nullptr, *d_large = nullptr;
   long long *d_wstart = nullptr, *d_wend = nullptr;
@@ -157,6 +163,10 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreate(&c->ev_plan));
+  CK(cudaEventCreate(&c->ev_plan0));
   c->stream = c->own_stream;
   for (int i = 0; i < NEV; ++i) CK(cudaEventCreate(&c->ev[i]));
   CKR(dev_alloc(&c->d_err, 1));
@@ -194,6 +204,7 @@ static void free_data(tdsfs_ctx* c) {
   c->keys_ready = c->tables_ready = c->results_ready = false;
   c->cand_W = -1;
   c->groups_mode = -1;
+  c->plan_W = -1;
 }
 
 extern "C" void tdsfs_destroy(tdsfs_t* c) {
@@ -214,6 +225,8 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
+  cudaStreamDestroy(c->plan_stream);
+  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_plan); cudaEventDestroy(c->ev_plan0);
   delete c;
 }
 
@@ -666,13 +679,9 @@ extern "C" int tdsfs_fetch_results(tdsfs_t* c, tdsfs_result_t* out, int64_t cap,
   return 0;
 }
 
-static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, int64_t cap, int64_t* n_windows) {
-  if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
-  if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
-  if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
-  CK(cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
-  if (c->cand_W != W || c->cand_snp != (int)snp_mode) {  // window plan cached per (size, mode): no sync in steady state
+// candidate list of (W, mode) on the device + K2 launch on stream `st`
+static int launch_bounds(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t st) {
+  if (c->cand_W != W || c->cand_snp != (int)snp_mode) {  // candidate offsets cached per (size, mode): no sync in steady state
     CKR(candidates(c, W, snp_mode, c->cand_off_host));
     CKR(ensure_windows(c, c->cand_off_host[c->C]));
     dev_free(c->d_cand_off);
@@ -682,9 +691,6 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     c->cand_snp = snp_mode;
   }
   const long long ncand = c->cand_off_host[c->C];
-  if (out && cap < ncand) return fail(TDSFS_ERR_ARG, "result capacity %lld < %lld candidate windows", (long long)cap, ncand);
-  CK(cudaEventRecord(c->ev[EV_SC0], st));
-  c->ncand = ncand;
   if (ncand > 0) {
     CK(cudaMemsetAsync(c->d_nlarge, 0, sizeof(int), st));
     WinParams w;
@@ -694,8 +700,47 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     const int g2 = (int)((ncand + 255) / 256);
     if (snp_mode) k2_bounds_snp<<<g2, 256, 0, st>>>(w); else k2_bounds_bp<<<g2, 256, 0, st>>>(w);
     c->launches++;
-    CK(cudaEventRecord(c->ev[EV_K2], st));
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
 
+// Window boundaries depend on positions only: launch K2 on a side stream now so that it overlaps the count kernel and the
+// background all-reduce; the next scan of the same (size, mode) waits for it instead of launching K2 itself.
+static int plan(tdsfs_ctx* c, long long W, bool snp_mode) {
+  if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!c->dPos) return fail(TDSFS_ERR_STATE, "load data first");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev_fork, c->stream));            // after everything queued so far (previous scan reads the old plan)
+  CK(cudaStreamWaitEvent(c->plan_stream, c->ev_fork, 0));
+  CK(cudaEventRecord(c->ev_plan0, c->plan_stream));
+  CKR(launch_bounds(c, W, snp_mode, c->plan_stream));
+  CK(cudaEventRecord(c->ev_plan, c->plan_stream));
+  c->plan_W = W;
+  c->plan_snp = snp_mode;
+  c->results_ready = false;
+  return 0;
+}
+extern "C" int tdsfs_plan_bp(tdsfs_t* c, int64_t W) { return plan(c, W, false); }
+extern "C" int tdsfs_plan_snp(tdsfs_t* c, int64_t N) { return plan(c, N, true); }
+
+static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, int64_t cap, int64_t* n_windows) {
+  if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const bool planned = c->plan_W == W && c->plan_snp == (int)snp_mode;
+  c->plan_W = -1;
+  CK(cudaEventRecord(c->ev[EV_SC0], st));
+  if (planned) CK(cudaStreamWaitEvent(st, c->ev_plan, 0));   // K2 already ran (or is running) on the side stream
+  else CKR(launch_bounds(c, W, snp_mode, st));
+  c->planned_last = planned;
+  const long long ncand = c->cand_off_host[c->C];
+  if (out && cap < ncand) return fail(TDSFS_ERR_ARG, "result capacity %lld < %lld candidate windows", (long long)cap, ncand);
+  c->ncand = ncand;
+  CK(cudaEventRecord(c->ev[EV_K2], st));
+  if (ncand > 0) {
     ScoreParams s;
     memset(&s, 0, sizeof s);
     s.rec = c->d_rec; s.flags = c->dFlags; s.wlo = c->d_wlo; s.whi = c->d_whi; s.wchrom = c->d_wchrom;
@@ -738,7 +783,6 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     CK(cudaEventRecord(c->ev[EV_K3L], st));
     CK(cudaGetLastError());
   } else {
-    CK(cudaEventRecord(c->ev[EV_K2], st));
     CK(cudaEventRecord(c->ev[EV_K3S], st));
     CK(cudaEventRecord(c->ev[EV_K3L], st));
   }
@@ -770,7 +814,8 @@ extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
   const bool was_sync = c->sync;
   c->sync = false;  // at most one synchronisation, at the end of the whole pass
-  int r = tdsfs_background(c, bg_mode, 0, -1, -1);
+  int r = plan(c, W, false);  // K2 on the side stream, concurrent with the count kernel
+  if (!r) r = tdsfs_background(c, bg_mode, 0, -1, -1);
   if (!r) r = tdsfs_finalize_background(c);
   if (!r) r = scan(c, W, false, out, cap, n);
   c->sync = was_sync;
@@ -880,7 +925,8 @@ extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
   if (c->keys_ready) cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
   if (c->fin_timed) cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
   if (c->results_ready) {
-    cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
+    if (c->planned_last) cudaEventElapsedTime(&c->ms[2], c->ev_plan0, c->ev_plan);  // K2 ran on the side stream
+    else cudaEventElapsedTime(&c->ms[2], c->ev[EV_SC0], c->ev[EV_K2]);
     cudaEventElapsedTime(&c->ms[3], c->ev[EV_K2], c->ev[EV_K3S]);
     cudaEventElapsedTime(&c->ms[4], c->ev[EV_K3S], c->ev[EV_K3L]);
     cudaEventElapsedTime(&c->ms[6], c->ev[EV_SC0], c->ev[EV_K3L]);

@@ -18,7 +18,7 @@ ERR_RANGE = 4
 EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
-    "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
+    "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_poisson_score",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_version",
@@ -177,6 +177,11 @@ class Handle:
         self._check(self._L.tdsfs_finalize_background(self._h))
 
     # ---- scans
+    def plan(self, size, snp_mode=False):
+        """Launch the window-boundary kernel ahead of the scan, on a side stream (overlaps background + all-reduce)."""
+        f = self._L.tdsfs_plan_snp if snp_mode else self._L.tdsfs_plan_bp
+        self._check(f(self._h, C.c_int64(size)))
+
     def candidates(self, size, snp_mode=False):
         n = C.c_int64()
         f = self._L.tdsfs_candidates_snp if snp_mode else self._L.tdsfs_candidates_bp

@@ -69,6 +69,7 @@ def gather_results(local, chrom_base, group=None):
 def sharded_scan_bp(handle, window_bp, bg_mode, device, group=None, chrom_base=0):
     """background -> (all-reduce) -> finalize -> scan -> gather, for a handle that already holds this rank's shard."""
     import tdsfs_capi as T
+    handle.plan(window_bp)  # window boundaries on a side stream: overlaps the count kernel and the all-reduce
     handle.background(bg_mode)
     if bg_mode in (T.BG_GENOME, T.BG_CHROM):
         allreduce_background(background_tensor(handle, device), group)

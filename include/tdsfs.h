@@ -145,6 +145,10 @@ int tdsfs_finalize_background(tdsfs_t* ctx);
  * TDSFS_F_EMPTY) and fixed-SNP windows (:1515-1535: full chunks of N SNPs, partial tail dropped).
  * `out` may be NULL: results then stay on the device (tdsfs_fetch_results copies them later); cap = capacity of
  * the out arrays; *n_windows = number of candidate windows written. */
+/* Optional: launch the window-boundary kernel NOW on a side stream (it depends on positions only), so that it overlaps
+ * tdsfs_background and the multi-GPU all-reduce; the next tdsfs_scan_* of the same size waits for it instead of launching it. */
+int tdsfs_plan_bp(tdsfs_t* ctx, int64_t W);
+int tdsfs_plan_snp(tdsfs_t* ctx, int64_t N);
 int tdsfs_candidates_bp(tdsfs_t* ctx, int64_t W, int64_t* n_candidates);
 int tdsfs_candidates_snp(tdsfs_t* ctx, int64_t N, int64_t* n_candidates);
 int tdsfs_scan_bp(tdsfs_t* ctx, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
