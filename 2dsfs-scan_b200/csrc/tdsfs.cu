@@ -697,6 +697,8 @@ static int launch_bounds(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t 
     w.pos = c->dPos; w.chrom_off = c->d_off; w.cand_off = c->d_cand_off; w.C = c->C; w.W = W; w.ncand = ncand;
     w.wlo = c->d_wlo; w.whi = c->d_whi; w.wchrom = c->d_wchrom; w.wstart = c->d_wstart; w.wend = c->d_wend;
     w.large = c->d_large; w.nlarge = c->d_nlarge;
+    w.r_count = c->r_count; w.r_flags = c->r_flags;
+    w.wcap = score_small_ok(c->n1, c->n2, c->bins2d) && score_group_smem_words(c->n1, c->n2) * 4 <= 200 * 1024 ? WCAP : 0;
     const int g2 = (int)((ncand + 255) / 256);
     if (snp_mode) k2_bounds_snp<<<g2, 256, 0, st>>>(w); else k2_bounds_bp<<<g2, 256, 0, st>>>(w);
     c->launches++;
@@ -750,25 +752,24 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
     // small windows: one warp each
-    if (!score_small_ok(c->n1, c->n2, c->bins2d)) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer (n <= 1023 per population)");
-    // groups of G warps per window; G = 4 keeps the shared-memory footprint per window and quadruples the resident warps
+    // small windows: groups of G warps per window over shared-memory tables (skipped for panels beyond their limits:
+    // K2 then lists every window as "large")
     const int gwords = score_group_smem_words(c->n1, c->n2);
-    if (gwords * 4 > 220 * 1024) return fail(TDSFS_ERR_ARG, "panel too large for the window scorer");
-    int G = c->score_group_warps;
-    if (const char* e = getenv("TDSFS_SCORE_G")) G = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);  // tuning knob
-    while (G > 1 && (SCORE_WARPS / G) * gwords * 4 * 1 > 220 * 1024) G /= 2;
-    int groups = SCORE_WARPS / G;
-    while (groups > 1 && groups * gwords * 4 > 220 * 1024) groups /= 2;  // (only for very large panels)
-    const int smem = (SCORE_WARPS / G) * gwords * 4;
-    void (*sk)(ScoreParams) = G == 4 ? k3_score_small<4> : (G == 2 ? k3_score_small<2> : k3_score_small<1>);
-    CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sk, SCORE_WARPS * 32, smem));
-    occ = std::max(1, occ);
-    const long long want = (ncand + (SCORE_WARPS / G) - 1) / (SCORE_WARPS / G);
-    const int grid = (int)std::min<long long>(want, (long long)c->sm_count * occ);
-    sk<<<grid, SCORE_WARPS * 32, smem, st>>>(s);
-    c->launches++;
+    if (score_small_ok(c->n1, c->n2, c->bins2d) && gwords * 4 <= 200 * 1024) {
+      int G = c->score_group_warps;
+      if (const char* e = getenv("TDSFS_SCORE_G")) G = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);  // tuning knob
+      while (G < SCORE_WARPS && (SCORE_WARPS / G) * gwords * 4 > 200 * 1024) G *= 2;  // fewer, wider groups for big panels
+      const int smem = (SCORE_WARPS / G) * gwords * 4;
+      void (*sk)(ScoreParams) = G >= 8 ? k3_score_small<8> : (G == 4 ? k3_score_small<4> : (G == 2 ? k3_score_small<2> : k3_score_small<1>));
+      CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sk, SCORE_WARPS * 32, smem));
+      occ = std::max(1, occ);
+      const long long want = (ncand + (SCORE_WARPS / G) - 1) / (SCORE_WARPS / G);
+      const int grid = (int)std::min<long long>(want, (long long)c->sm_count * occ);
+      sk<<<grid, SCORE_WARPS * 32, smem, st>>>(s);
+      c->launches++;
+    }
     CK(cudaEventRecord(c->ev[EV_K3S], st));
     // large windows: one CTA each over dense global scratch
     const long long sstride = (long long)c->bins2d + c->n1 + 1 + c->n2 + 1;

@@ -554,8 +554,11 @@ struct WinParams {
   int32_t* wchrom;
   long long* wstart;
   long long* wend;
-  int32_t* large;             // ids of windows with more than WCAP SNPs
+  int32_t* large;             // ids of windows with more than `wcap` SNPs
   int* nlarge;
+  int32_t* r_count;           // result arrays: K2 marks empty candidates itself
+  uint8_t* r_flags;
+  int wcap;                   // WCAP, or 0 when the panel is too large for the shared-memory scorer (every window "large")
 };
 
 __device__ __forceinline__ long long lower_bound_pos(const int32_t* pos, long long lo, long long hi, long long v) {
@@ -587,9 +590,10 @@ __global__ void __launch_bounds__(256) k2_bounds_bp(const __grid_constant__ WinP
   p.wlo[id] = (int32_t)lo;
   p.whi[id] = (int32_t)hi;
   p.wchrom[id] = c;
+  if (hi == lo) { p.r_count[id] = 0; p.r_flags[id] = TDSFS_F_EMPTY; }  // the reference never emits an empty window
   p.wstart[id] = 1 + k * p.W;
   p.wend[id] = (k + 1) * p.W;
-  if (hi - lo > WCAP) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
+  if (hi - lo > p.wcap) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
 }
 
 // fixed-SNP: chunk j of a chromosome = rows [off + jN, off + (j+1)N); label per :1527/:1535
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(256) k2_bounds_snp(const __grid_constant__ Win
   p.wchrom[id] = c;
   p.wstart[id] = j == 0 ? (long long)__ldg(p.pos + lo) : (long long)__ldg(p.pos + lo - 1) + 1;
   p.wend[id] = (long long)__ldg(p.pos + hi - 1);
-  if (hi - lo > WCAP) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
+  if (hi - lo > p.wcap) p.large[atomicAdd(p.nlarge, 1)] = (int32_t)id;
 }
 
 // ------------------------------------------------------------------------------------------------ K3+K4 scoring
@@ -691,8 +695,8 @@ __device__ __forceinline__ void write_result(const ScoreParams& p, long long id,
 constexpr int SCORE_WARPS = 8;
 constexpr int KEY_SHIFT = 10;  // multiplicity field (< 1024, WCAP = 768)
 __host__ __device__ inline int score_group_smem_words(int n1, int n2) {
-  // table | 1D bins (padded to an even word count) | reduction scratch (4 warps x 10 words)
-  return HASH_SLOTS + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + 4 * 10;
+  // table | 1D bins (padded to an even word count) | reduction scratch (SCORE_WARPS x 10 words)
+  return HASH_SLOTS + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + SCORE_WARPS * 10;
 }
 // limits of the shared-memory scorer; panels beyond them are scored by the CTA kernel only
 __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   uint32_t* h1a = tab + HASH_SLOTS;            // packed 16-bit bins: bin f in word f >> 1, half f & 1
   const int nw1 = (p.n1 + 2) / 2, nw2 = (p.n2 + 2) / 2;
   uint32_t* h1b = h1a + nw1;
-  uint32_t* red = h1a + ((nw1 + nw2 + 1) & ~1);  // [4][10] (8-byte aligned): per warp {a2, a1a, a1b (doubles), N-pack, count, nall}
+  uint32_t* red = h1a + ((nw1 + nw2 + 1) & ~1);  // [G][10] (8-byte aligned): per warp {a2, a1a, a1b (doubles), N-pack, count, nall}
   auto gsync = [&]() {
     if (G == 1) __syncwarp(); else named_bar_sync(1 + grp, GT);
   };

@@ -302,3 +302,25 @@ def test_synthetic_generator_statistics(T, h):
     assert cnt.min() >= 0 and (cnt[:, 0] + cnt[:, 1] <= 2 * ns1).all()
     # spectrum is dominated by rare variants (log-uniform ancestral frequency)
     assert (cnt[:, 1] <= 40).mean() > 0.5
+
+
+def test_panel_beyond_shared_memory_scorer_limits(T, h):
+    """(2n1+1)(2n2+1) >= 2^22 bins: every window goes through the CTA scorer with dense global scratch."""
+    rng = np.random.default_rng(5)
+    n1 = n2 = 1100
+    S = 3000
+    cnt = np.zeros((S, 4), dtype=np.uint16)
+    for p, n in ((0, n1), (1, n2)):
+        called = 2 * n - 2 * rng.binomial(n, 0.02, S)
+        alt = rng.binomial(called, np.exp(rng.uniform(np.log(0.001), np.log(0.999), S)))
+        cnt[:, 2 * p], cnt[:, 2 * p + 1] = called - alt, alt
+    pos = np.sort(rng.choice(np.arange(1, 100000), size=S, replace=False)).astype(np.int32)
+    off = np.array([0, 1000, S])
+    h.set_panel(n1, n2, True)
+    h.load_counts(cnt, pos, off)
+    res = h.run_bp(T.BG_PER_CHROM, 10000)
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(GOLDEN), "..", "oracle")])
+    import sfs_oracle_c as OC
+    exp = OC.scan(cnt, pos, off, n1, n2, W=10000, bg="per_chrom", nthreads=4)
+    compare_scan(T, res, exp)
