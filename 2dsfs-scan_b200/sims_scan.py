@@ -86,6 +86,18 @@ def get_gens(main_dir):
     return search_strings
 
 
+def _unguarded(T2D, T1, T2_, pop1_size, pop2_size):
+    """The twins have no None guards: an empty spectrum divides by zero (:348, :415) -- except a 1D spectrum of a single
+    diploid, whose interior is empty: nothing is divided and scipy's logpmf of empty vectors gives NaN."""
+    if pop1_size <= 1:
+        T1 = float("nan")
+    if pop2_size <= 1:
+        T2_ = float("nan")
+    if T2D is None or T1 is None or T2_ is None:
+        raise ZeroDivisionError("division by zero")
+    return T2D, T1, T2_
+
+
 def process_window(data_dict, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_size, pop1, pop2, pop1_size, pop2_size, start_position,
                    end_position, variant_type):
     """reference :451-590: fixed-bp scan of one replicate against precomputed backgrounds."""
@@ -107,8 +119,7 @@ def process_window(data_dict, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_size, pop1
     T2, Ta, Tb = stat_lists(res, live)
     results = {}
     for k, c, st, T2D, T1, T2_ in zip(keys, counts, starts, T2, Ta, Tb):
-        if T2D is None or T1 is None or T2_ is None:
-            raise ZeroDivisionError("division by zero")  # count / total_fg with an empty spectrum (:415, :348)
+        T2D, T1, T2_ = _unguarded(T2D, T1, T2_, pop1_size, pop2_size)
         results[k] = {"window_type": "background" if 0 <= st < 500000 else "foreground", "window_start": st,
                       "window_end": st + window_size, "snp_count": c, "T2D": T2D, "T1D_p1": T1, "T1D_p2": T2_,
                       "new_term_p1": T2D - T1, "new_term_p2": T2D - T2_, "T2D_diff": T2D - (T1 - T2_) / 2}
@@ -145,8 +156,7 @@ def process_window_batch(data_dicts, bg_2d_sfs, bg_p1_sfs, bg_p2_sfs, window_siz
     T2, Ta, Tb = stat_lists(res, live)
     for ci, c, st, en, T2D, T1, T2_ in zip(res["chrom"][live].tolist(), res["snp_count"][live].tolist(), res["start"][live].tolist(),
                                            res["end"][live].tolist(), T2, Ta, Tb):
-        if T2D is None or T1 is None or T2_ is None:
-            raise ZeroDivisionError("division by zero")
+        T2D, T1, T2_ = _unguarded(T2D, T1, T2_, pop1_size, pop2_size)
         r, chrom = big.chroms[ci]
         out[r][f"{chrom} {st}-{en}"] = {"window_type": "background" if 0 <= st < 500000 else "foreground", "window_start": st,
                                         "window_end": st + window_size, "snp_count": c, "T2D": T2D, "T1D_p1": T1, "T1D_p2": T2_,

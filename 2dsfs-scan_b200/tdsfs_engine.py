@@ -130,6 +130,9 @@ class Engine:
         bins = sorted(fg.keys())[1:-1]
         x = [int(fg[k]) for k in bins]
         n = sum(x)
+        if not bins and not guarded:
+            # an empty interior (1D spectrum of a single diploid) never divides: scipy's logpmf of empty vectors is NaN
+            return math.nan
         if n == 0:
             if guarded:
                 return None
