@@ -90,6 +90,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// same, with an L2 evict-first policy: the genotype matrix is streamed once and must not displace the background tables
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -321,7 +329,7 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
       }
     }
   }
-  p.rec[s] = make_uint2(key, alts);
+  __stcs(p.rec + s, make_uint2(key, alts));  // streaming store: read once by the scorer, from L2 or HBM
 }
 
 // flush the CTA-private histograms of group g into global memory (threads tid..nthr of the sink group)
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
       const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
       const uint32_t bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
       mbar_arrive_expect_tx(my_full + slot, bytes);
-      bulk_g2s(my_stages + (size_t)slot * p.stage_bytes, p.G + blk0 * block_words, bytes, my_full + slot);
+      bulk_g2s_stream(my_stages + (size_t)slot * p.stage_bytes, p.G + blk0 * block_words, bytes, my_full + slot);
     };
     if (lane == 0)
       for (int j = 0; j < depth; ++j)
