@@ -498,6 +498,8 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
     if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
     else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    p.interleave = (p.bg_group == nullptr) ? 1 : 0;
+    if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
     for (auto& ch : c->chunks) {
       if (ch.r1 <= ch.r0) continue;
       if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));

@@ -55,6 +55,8 @@ struct KeyParams {
   int nstage, stage_bytes;  // K1 ring: stages of `tile_blocks` 32-SNP blocks; nstage is a multiple of cwarps
   int tile_blocks;
   int cwarps;               // active consumer warps (<= K1_CWARPS)
+  int interleave;           // 1: tile i of the launch goes to CTA i % grid (all SMs stream one moving window of the matrix);
+                            // 0: contiguous tile range per CTA (keeps a CTA inside one background group)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -389,9 +391,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
   // contiguous range of tiles of this CTA; a tile = tile_blocks blocks of 32 SNPs
   const long long b0 = p.r0 / BLK, b1 = (p.r1 + BLK - 1) / BLK;  // r0 is a multiple of BLK
   const long long ntiles = (b1 - b0 + p.tile_blocks - 1) / p.tile_blocks;
-  const long long t0 = ntiles * blockIdx.x / gridDim.x;
-  const long long t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-  const long long n = t1 - t0;
+  // tile `i` (local index) of this CTA is global tile t0 + i * tstride
+  const long long t0 = p.interleave ? blockIdx.x : ntiles * blockIdx.x / gridDim.x;
+  const long long tstride = p.interleave ? gridDim.x : 1;
+  const long long n = p.interleave ? (ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0)
+                                   : ntiles * (blockIdx.x + 1) / gridDim.x - t0;
   const long long block_words = (long long)RW * BLK;
   const int depth = p.nstage / p.cwarps;  // stages per warp
 
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
     uint8_t* my_stages = stages + (size_t)warp * depth * p.stage_bytes;
     uint64_t* my_full = full + warp * depth;
     auto issue = [&](long long i, int slot) {  // lane 0 only
-      const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+      const long long blk0 = b0 + (t0 + i * tstride) * p.tile_blocks;
       const uint32_t bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
       mbar_arrive_expect_tx(my_full + slot, bytes);
       bulk_g2s_stream(my_stages + (size_t)slot * p.stage_bytes, p.G + blk0 * block_words, bytes, my_full + slot);
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
     int slot = 0;
     uint32_t ph = 0;
     for (long long i = warp; i < n; i += p.cwarps) {
-      const long long blk0 = b0 + (t0 + i) * p.tile_blocks;
+      const long long blk0 = b0 + (t0 + i * tstride) * p.tile_blocks;
       const int nb = (int)min((long long)p.tile_blocks, b1 - blk0);
       mbar_wait(my_full + slot, ph);
       const uint32_t* tile = reinterpret_cast<const uint32_t*>(my_stages + (size_t)slot * p.stage_bytes);
