@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = base + q * GT + tg;
-        r[q] = i < cnt ? __ldg(p.rec + lo + i) : make_uint2(0u, 0u);
+        r[q] = i < cnt ? __ldcs(p.rec + lo + i) : make_uint2(0u, 0u);  // streamed once: keep the ln b table in L2
         if (has_flags && i < cnt) count += (__ldg(p.flags + lo + i) >> 1) & 1;
       }
 #pragma unroll
