@@ -121,41 +121,45 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arms (oracle)
 def numpy_panel(cfg, rows, seed):
-    """Host-side synthetic panel with the distribution family of the device generator (used when no GPU is present)."""
-    sys.path.insert(0, PKG)
-    from tdsfs_pack import pack_codes
+    """Host-side synthetic panel with the distribution family of the device generator (log-uniform ancestral frequency,
+    per-population drift with F = 0.05, Binomial(2, p) calls, 2 % missing), generated in chunks.  Used by the reference arm,
+    which must not touch libtdsfs at all."""
+    from tdsfs_pack import _pack_block, to_b32
     rng = np.random.default_rng(seed)
     n1, n2 = cfg["n1"], cfg["n2"]
     lo, hi = 1.0 / (4.0 * (n1 + n2)), 1.0 - 1.0 / (4.0 * (n1 + n2))
-    pa = lo * np.exp(rng.random(rows) * np.log(hi / lo))
+    out = []
+    for r0 in range(0, rows, 32768):
+        m = min(32768, rows - r0)
+        pa = lo * np.exp(rng.random(m) * np.log(hi / lo))
+        blocks = []
+        for ns in (n1, n2):
+            p = np.clip(pa + rng.normal(0, 1, m) * np.sqrt(0.05 * pa * (1 - pa)), 0, 1).astype(np.float32)[:, None]
+            a = (rng.random((m, ns), dtype=np.float32) < p).astype(np.uint8) + (rng.random((m, ns), dtype=np.float32) < p).astype(np.uint8)
+            c = np.where(a == 2, 3, a).astype(np.uint8)
+            c[rng.random((m, ns), dtype=np.float32) < 0.02] = 2
+            blocks.append(_pack_block(c))
+        out.append(np.concatenate(blocks, axis=1))
+    return to_b32(np.concatenate(out, axis=0))
 
-    def codes(ns):
-        p = np.clip(pa + rng.normal(0, 1, rows) * np.sqrt(0.05 * pa * (1 - pa)), 0, 1)[:, None]
-        a = (rng.random((rows, ns), dtype=np.float32) < p).astype(np.uint8) + (rng.random((rows, ns), dtype=np.float32) < p).astype(np.uint8)
-        c = np.where(a == 2, 3, a).astype(np.uint8)
-        c[rng.random((rows, ns), dtype=np.float32) < 0.02] = 2
-        return c
 
-    G, _, _ = pack_codes(codes(n1), codes(n2))
-    return G
-
-
-def sample_panel(cfg, rows):
-    """First `rows` SNP rows of chromosome 0 of the workload: device generator when a GPU is present (identical bytes to the
-    GPU arm's input), numpy otherwise.  Input generation only -- never part of a timed CPU region."""
+def sample_panel(cfg, rows, allow_gpu=True):
+    """First `rows` SNP rows of chromosome 0 of the workload: device generator when allowed and a GPU is present (identical
+    bytes to the GPU arm's input), numpy otherwise.  Input generation only -- never part of a timed CPU region."""
     w1, w2 = words_for(cfg["n1"]), words_for(cfg["n2"])
-    try:
-        import torch
-        if torch.cuda.is_available():
-            import tdsfs_capi as T
-            h = T.Handle(0)
-            g = torch.empty(((rows + 31) // 32 * (w1 + w2) * 32,), dtype=torch.int32, device="cuda:0")
-            h.synth_genotypes(g.data_ptr(), rows, 0, w1, w2, cfg["n1"], cfg["n2"], cfg["seed"])
-            G = g.cpu().numpy().view(np.uint32)
-            h.close()
-            return G, "device generator"
-    except Exception:  # noqa: BLE001
-        pass
+    if allow_gpu:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                import tdsfs_capi as T
+                h = T.Handle(0)
+                g = torch.empty(((rows + 31) // 32 * (w1 + w2) * 32,), dtype=torch.int32, device="cuda:0")
+                h.synth_genotypes(g.data_ptr(), rows, 0, w1, w2, cfg["n1"], cfg["n2"], cfg["seed"])
+                G = g.cpu().numpy().view(np.uint32)
+                h.close()
+                return G, "device generator"
+        except Exception:  # noqa: BLE001
+            pass
     return numpy_panel(cfg, rows, cfg["seed"]), "numpy generator"
 
 
@@ -180,19 +184,19 @@ def cpu_pass(OC, G, pos, cfg, nthreads):
     return time.perf_counter() - t, len(r["start"])
 
 
-def cpu_sample_rate(cfg, budget_s, nthreads, steps=1, warmup=0):
+def cpu_sample_rate(cfg, budget_s, nthreads, steps=1, warmup=0, allow_gpu=True):
     """Time the oracle port on a bounded sample sized (by a pilot) to ~budget_s per step.  Returns dict."""
     OC = oracle_modules()
     nthreads = nthreads or OC.max_threads()
     pos_all = positions_for(cfg, [0])[0]
     per_win = cfg["W"] // cfg["mean_gap"]
     pilot_rows = min(len(pos_all), per_win * max(2 * nthreads, 8))
-    G, gen = sample_panel(cfg, pilot_rows)
+    G, gen = sample_panel(cfg, pilot_rows, allow_gpu)
     t_pilot, nwin = cpu_pass(OC, G, pos_all[:pilot_rows], cfg, nthreads)
     rate = pilot_rows / t_pilot
     rows = int(min(len(pos_all), max(pilot_rows, rate * budget_s)))
     if rows != pilot_rows:
-        G, gen = sample_panel(cfg, rows)
+        G, gen = sample_panel(cfg, rows, allow_gpu)
     pos = pos_all[:rows]
     times = []
     for i in range(warmup + steps):
@@ -212,7 +216,7 @@ def run_reference(args, cfg):
         return
     total_budget = 150.0
     per_step = max(2.0, total_budget / (args.steps + args.warmup + 1))
-    cb, rows, times = cpu_sample_rate(cfg, per_step, 0, steps=args.steps, warmup=args.warmup)
+    cb, rows, times = cpu_sample_rate(cfg, per_step, 0, steps=args.steps, warmup=args.warmup, allow_gpu=False)
     line = {"impl": "reference", "metric": "SNPs/sec, 2D-SFS + T2D/T1D 20 kb window scan", "value": cb["value"], "unit": "SNPs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
