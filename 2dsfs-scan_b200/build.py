@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libtdsfs.so")
 PACKER = os.path.join(HERE, "lib", "libtdsfs_pack.so")
+DICTCONV = os.path.join(HERE, "lib", "libtdsfs_dictconv.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "1886"]
 
@@ -32,6 +33,10 @@ def build(force=False, verbose=False):
     pack_src = os.path.join(SRC, "vcf_pack.cpp")
     if os.path.exists(pack_src) and (force or _newer(PACKER, [pack_src])):
         subprocess.check_call(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", PACKER, pack_src, "-lz"])
+    conv_src = os.path.join(SRC, "dictconv.c")
+    if os.path.exists(conv_src) and (force or _newer(DICTCONV, [conv_src])):
+        import sysconfig
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], "-o", DICTCONV, conv_src])
     return LIB
 
 

@@ -15,6 +15,28 @@ import tdsfs_capi as T
 
 _EPS10 = float(np.finfo(np.float64).eps * 10)
 
+_conv = False
+
+
+def _dictconv():
+    """ctypes.PyDLL binding of lib/libtdsfs_dictconv.so (optional accelerator of the dict -> array conversion)."""
+    global _conv
+    if _conv is False:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtdsfs_dictconv.so")
+        _conv = None
+        if os.path.exists(path) and not os.environ.get("TDSFS_NO_DICTCONV"):
+            try:
+                f = ctypes.PyDLL(path).tdsfs_dict_to_arrays
+                f.restype = ctypes.c_int
+                f.argtypes = [ctypes.py_object, ctypes.py_object, ctypes.py_object, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.py_object, ctypes.py_object]
+                _conv = f
+            except OSError:
+                _conv = None
+    return _conv
+
 
 class SnpTable:
     """A data_dict in array form, sorted by (chromosome string, position) as every reference scanner sorts it
@@ -25,6 +47,41 @@ class SnpTable:
 
     @classmethod
     def from_dict(cls, data_dict, pop1, pop2):
+        conv = _dictconv()
+        if conv is not None and type(data_dict) is dict:
+            return cls._from_dict_c(conv, data_dict, pop1, pop2)
+        return cls._from_dict_py(data_dict, pop1, pop2)
+
+    @classmethod
+    def _from_dict_c(cls, conv, data_dict, pop1, pop2):
+        """The per-SNP loop in C (csrc/dictconv.c); same semantics and exceptions as _from_dict_py."""
+        n = len(data_dict)
+        pos = np.empty(n, dtype=np.int64)
+        cnt = np.zeros((n, 4), dtype=np.int64)
+        cidx = np.empty(n, dtype=np.int32)
+        aidx = np.empty(n, dtype=np.int32)
+        names, vocab = [], []
+        conv(data_dict, pop1, pop2, pos.ctypes.data, cnt.ctypes.data, cidx.ctypes.data, aidx.ctypes.data, names, vocab)
+        keys = list(data_dict.keys())
+        rank = np.argsort(np.argsort(np.array(names, dtype=object), kind="stable"), kind="stable") if names else np.zeros(0, np.int64)
+        cidx = rank[cidx] if n else cidx.astype(np.int64)
+        order = np.lexsort((pos, cidx))
+        self = cls()
+        self.chroms = sorted(names)
+        self.pos = pos[order]
+        self.cnt = cnt[order]
+        va = np.empty(len(vocab), dtype=object)
+        va[:] = vocab
+        self.ann = va[aidx][order] if n else np.array([], dtype=object)
+        self.keys = [keys[i] for i in order.tolist()]
+        self.off = np.concatenate([[0], np.cumsum(np.bincount(cidx, minlength=len(names)))]).astype(np.int64) if n else np.zeros(1, np.int64)
+        self.pops = (pop1, pop2)
+        self.n = n
+        self.last_key_row = int(np.flatnonzero(order == n - 1)[0]) if n else -1
+        return self
+
+    @classmethod
+    def _from_dict_py(cls, data_dict, pop1, pop2):
         n = len(data_dict)
         chrom = [None] * n
         pos = np.empty(n, dtype=np.int64)

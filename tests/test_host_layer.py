@@ -69,3 +69,27 @@ def test_cpp_packer_matches_reference_ingest():
             assert cnt[i].tolist() == list(ref[k][0]) + list(ref[k][1]), (k, cnt[i], ref[k])
             assert P.ann[i] == ref[k][2]
     assert P.n_records == P.n + P.n_skipped or stem == "ingest_small"
+
+
+def test_dictconv_c_path_equals_python_path():
+    """csrc/dictconv.c (per-SNP loop of the dict -> array conversion in C) == the pure-Python conversion, errors included."""
+    import pytest
+    import tdsfs_engine as E
+    from helpers import load_small, rows_to_dict
+    conv = E._dictconv()
+    if conv is None:
+        pytest.skip("libtdsfs_dictconv.so not built")
+    for case in load_small()["cases"]:
+        d = rows_to_dict(case["rows"], case["pops"])
+        a, b = E.SnpTable._from_dict_c(conv, d, "uv", "bv"), E.SnpTable._from_dict_py(d, "uv", "bv")
+        for f in ("chroms", "keys", "n", "last_key_row", "pops"):
+            assert getattr(a, f) == getattr(b, f), (case["name"], f)
+        for f in ("pos", "cnt", "off"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (case["name"], f)
+        assert list(a.ann) == list(b.ann)
+    for bad, exc in (({"a-b-5": {"calls": {}}}, ValueError), ({"nodash": {"calls": {}}}, ValueError), ({"c-x": {"calls": {}}}, ValueError),
+                     ({"c-5": {}}, KeyError)):
+        for fn in (lambda: E.SnpTable._from_dict_c(conv, bad, "uv", "bv"), lambda: E.SnpTable._from_dict_py(bad, "uv", "bv")):
+            with pytest.raises(exc):
+                fn()
+    assert E.SnpTable._from_dict_c(conv, {}, "a", "b").n == 0
