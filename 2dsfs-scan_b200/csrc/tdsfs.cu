@@ -644,6 +644,9 @@ extern "C" int tdsfs_candidates_snp(tdsfs_t* c, int64_t N, int64_t* n) {
 
 static int ensure_windows(tdsfs_ctx* c, long long n) {
   if (n <= c->cand_cap) return 0;
+  // growing: a previous asynchronous scan may still be using the old arrays
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->plan_stream));
   dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom); dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend);
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
   dev_free(c->r_T1b); dev_free(c->r_flags);

@@ -324,3 +324,57 @@ def test_panel_beyond_shared_memory_scorer_limits(T, h):
     import sfs_oracle_c as OC
     exp = OC.scan(cnt, pos, off, n1, n2, W=10000, bg="per_chrom", nthreads=4)
     compare_scan(T, res, exp)
+
+
+def test_capi_error_conventions(T, h):
+    """Return codes + tdsfs_last_error(): call-order violations, bad arguments, small result buffers -- never a crash."""
+    cnt = np.array([[2, 2, 2, 2], [3, 1, 1, 3], [4, 0, 2, 2]], dtype=np.uint16)
+    pos = np.array([5, 9, 40], dtype=np.int32)
+    with pytest.raises(T.TdsfsError) as e:   # no panel yet
+        h.load_counts(cnt, pos, [0, 3])
+    assert e.value.code == 3
+    with pytest.raises(T.TdsfsError) as e:
+        h.set_panel(0, 5, True)
+    assert e.value.code == 1
+    h.set_panel(2, 2, True)
+    with pytest.raises(T.TdsfsError) as e:   # background before data
+        h.background(T.BG_GENOME)
+    assert e.value.code == 3
+    with pytest.raises(T.TdsfsError) as e:   # chrom_off must end at S
+        h.load_counts(cnt, pos, [0, 2])
+    assert e.value.code == 1
+    h.load_counts(cnt, pos, [0, 3])
+    with pytest.raises(T.TdsfsError) as e:   # scan before background
+        h.scan(10)
+    assert e.value.code == 3
+    with pytest.raises(T.TdsfsError) as e:
+        h.background(7)
+    assert e.value.code == 1
+    with pytest.raises(T.TdsfsError) as e:   # background chromosome out of range
+        h.background(T.BG_CHROM, bg_chrom=4)
+    assert e.value.code == 1
+    h.background(T.BG_GENOME)
+    with pytest.raises(T.TdsfsError) as e:   # tables not built yet
+        h.scan(10)
+    assert e.value.code == 3
+    h.finalize_background()
+    # result capacity too small
+    import ctypes as C
+    arrs, r = h._alloc_result(1)
+    n = C.c_int64()
+    rc = h._L.tdsfs_scan_bp(h._h, C.c_int64(10), C.byref(r), C.c_int64(1), C.byref(n))
+    assert rc == 1 and b"capacity" in h._L.tdsfs_last_error()
+    res = h.scan(10)
+    assert len(res["start"]) == 4 and int(((res["flags"] & T.F_EMPTY) == 0).sum()) == 2
+    with pytest.raises(T.TdsfsError) as e:   # window index out of range
+        h.window_spectra(99)
+    assert e.value.code == 1
+    # unsorted fix-ups are rejected
+    G = np.zeros(32 * 2, dtype=np.uint32)
+    fix = np.array([(2, 0, 1, 0), (1, 0, 0, 1)], dtype=T.FIXUP_DTYPE)
+    with pytest.raises(T.TdsfsError) as e:
+        h.load_genotypes(G, 3, 1, 1, 2, 2, pos, [0, 3], fixups=fix)
+    assert e.value.code == 1
+    with pytest.raises(T.TdsfsError) as e:   # more sample columns than the words hold
+        h.load_genotypes(G, 3, 1, 1, 17, 2, pos, [0, 3])
+    assert e.value.code == 1
