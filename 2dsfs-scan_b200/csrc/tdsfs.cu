@@ -342,7 +342,7 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
   if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
   if (words1 < 1 || words2 < 1 || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
     return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d)", words1, words2, ns1, ns2);
-  if ((long long)(words1 + words2) * BLK * 4 > 32 * 1024) return fail(TDSFS_ERR_ARG, "row too wide: more than 4096 samples per SNP is not supported yet");
+  if (ns1 > 65535 / 2 || ns2 > 65535 / 2) return fail(TDSFS_ERR_ARG, "more than 32767 samples per population");
   CK(cudaSetDevice(c->device));
   free_data(c);
   const bool has_fix = fixups && n_fixups > 0;
@@ -486,29 +486,51 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   if (c->dG) {
     const int RW = c->W1 + c->W2;
     const int blk_bytes = RW * BLK * 4;
-    p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile: >= one 32-SNP block, ~4-8 KB
-    p.stage_bytes = p.tile_blocks * blk_bytes;
-    // ring = k stages per consumer warp (k >= 2 when they fit): one being counted, the others in flight from HBM
-    const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
-    if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
-    p.cwarps = std::min(K1_CWARPS, fit);
-    p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));  // `depth` stages per warp
-    const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
-    void (*kern)(KeyParams) = k1_genotypes<0, 0>;
-    if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
-    else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    p.interleave = (p.bg_group == nullptr) ? 1 : 0;
-    if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
-    for (auto& ch : c->chunks) {
-      if (ch.r1 <= ch.r0) continue;
-      if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
-      p.r0 = ch.r0; p.r1 = ch.r1;
-      const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
-      const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
-      const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
-      kern<<<grid, K1_THREADS, smem, st>>>(p);
-      c->launches++;
+    if (blk_bytes > 32 * 1024) {
+      // wide rows (> 4096 samples): stream every 32-SNP block as segments of 64 words (8 KB)
+      const int seg_words = 64;
+      p.tile_blocks = 1;
+      p.stage_bytes = seg_words * BLK * 4;
+      const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
+      p.cwarps = std::min(K1_CWARPS, fit / 2);
+      p.nstage = p.cwarps * 2;
+      p.interleave = 0;
+      const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
+      CK(cudaFuncSetAttribute(k1_genotypes_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      for (auto& ch : c->chunks) {
+        if (ch.r1 <= ch.r0) continue;
+        if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
+        p.r0 = ch.r0; p.r1 = ch.r1;
+        const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
+        const int grid = (int)std::min<long long>(nblk, (long long)c->sm_count);
+        k1_genotypes_wide<<<grid, K1_THREADS, smem, st>>>(p, seg_words);
+        c->launches++;
+      }
+    } else {
+      p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile: >= one 32-SNP block, ~4-8 KB
+      p.stage_bytes = p.tile_blocks * blk_bytes;
+      // ring = k stages per consumer warp (k >= 2 when they fit): one being counted, the others in flight from HBM
+      const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
+      if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
+      p.cwarps = std::min(K1_CWARPS, fit);
+      p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));  // `depth` stages per warp
+      const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
+      void (*kern)(KeyParams) = k1_genotypes<0, 0>;
+      if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
+      else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      p.interleave = (p.bg_group == nullptr) ? 1 : 0;
+      if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
+      for (auto& ch : c->chunks) {
+        if (ch.r1 <= ch.r0) continue;
+        if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
+        p.r0 = ch.r0; p.r1 = ch.r1;
+        const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
+        const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
+        const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
+        kern<<<grid, K1_THREADS, smem, st>>>(p);
+        c->launches++;
+      }
     }
   } else {
     p.r0 = 0; p.r1 = c->S;

@@ -451,6 +451,87 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
   sink_flush(p, sm, cta_group, tid, K1_THREADS);
 }
 
+// K1 for rows wider than one ring stage (more than 4096 samples): a 32-SNP block is streamed as segments of `seg_words`
+// words (contiguous in the B32 layout); the warp carries its bit-sliced counters across the segments of a block and
+// sinks the SNPs after the last one.  Generic (runtime) geometry: the population of a word is decided per segment piece.
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes_wide(const __grid_constant__ KeyParams p, int seg_words) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W1 = p.W1, W2 = p.W2, RW = W1 + W2;
+  const int nseg = (RW + seg_words - 1) / seg_words;
+  uint8_t* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
+  SinkSmem sm;
+  sm.corner = reinterpret_cast<uint32_t*>(full + p.nstage);
+  sm.h1a = sm.corner + p.cr * p.cc;
+  sm.h1b = sm.h1a + p.h1a;
+  const int nhist = p.cr * p.cc + p.h1a + p.h1b;
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
+  __syncthreads();
+  const long long b0 = p.r0 / BLK, b1 = (p.r1 + BLK - 1) / BLK;
+  const long long nblk = b1 - b0;
+  const long long t0 = nblk * blockIdx.x / gridDim.x, t1 = nblk * (blockIdx.x + 1) / gridDim.x;
+  const long long block_words = (long long)RW * BLK;
+  const int depth = p.nstage / p.cwarps;
+  ChromCache cc;
+  const int cta_group = (t1 > t0) ? tile_group(p, p.r0 + t0 * BLK, cc) : -1;
+  if (warp < p.cwarps) {
+    uint8_t* my_stages = stages + (size_t)warp * depth * p.stage_bytes;
+    uint64_t* my_full = full + warp * depth;
+    // warp w owns blocks t0 + w, t0 + w + cwarps, ...; its item j = (own block j / nseg, segment j % nseg)
+    const long long my_blocks = (t1 - t0 > warp) ? (t1 - t0 - warp + p.cwarps - 1) / p.cwarps : 0;
+    const long long my_items = my_blocks * nseg;
+    auto issue = [&](long long j, int slot) {  // lane 0 only
+      const long long blk = b0 + t0 + warp + (j / nseg) * p.cwarps;
+      const int sg = (int)(j % nseg);
+      const int w0 = sg * seg_words, nw = min(seg_words, RW - w0);
+      const uint32_t bytes = (uint32_t)nw * BLK * 4;
+      mbar_arrive_expect_tx(my_full + slot, bytes);
+      bulk_g2s_stream(my_stages + (size_t)slot * p.stage_bytes, p.G + blk * block_words + (long long)w0 * BLK, bytes, my_full + slot);
+    };
+    if (lane == 0)
+      for (int j = 0; j < depth && j < my_items; ++j) issue(j, j);
+    int slot = 0;
+    uint32_t ph = 0;
+    PopCounts pc1, pc2;
+    for (long long j = 0; j < my_items; ++j) {
+      const int sg = (int)(j % nseg);
+      const int w0 = sg * seg_words, nw = min(seg_words, RW - w0);
+      mbar_wait(my_full + slot, ph);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(my_stages + (size_t)slot * p.stage_bytes) + lane;
+      // words [w0, w0+nw): the part below W1 belongs to population 1, the rest to population 2
+      const int n1w = max(0, min(nw, W1 - w0));
+      for (int w = 0; w < n1w; w += 4)
+        pc1.chunk4(q[w * BLK], w + 1 < n1w ? q[(w + 1) * BLK] : 0u, w + 2 < n1w ? q[(w + 2) * BLK] : 0u, w + 3 < n1w ? q[(w + 3) * BLK] : 0u);
+      for (int w = n1w; w < nw; w += 4)
+        pc2.chunk4(q[w * BLK], w + 1 < nw ? q[(w + 1) * BLK] : 0u, w + 2 < nw ? q[(w + 2) * BLK] : 0u, w + 3 < nw ? q[(w + 3) * BLK] : 0u);
+      __syncwarp();
+      if (lane == 0 && j + depth < my_items) {
+        fence_proxy_async();
+        issue(j + depth, slot);
+      }
+      if (++slot == depth) { slot = 0; ph ^= 1; }
+      if (sg == nseg - 1) {  // last segment of the block: sink its 32 SNPs
+        const long long s = (b0 + t0 + warp + (j / nseg) * p.cwarps) * BLK + lane;
+        if (s < p.r1) {
+          const uint32_t T1 = pc1.bits.total(), M1 = pc1.miss.total(), T2 = pc2.bits.total(), M2 = pc2.miss.total();
+          const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
+          const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
+          sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+        }
+        pc1 = PopCounts();
+        pc2 = PopCounts();
+      }
+    }
+  }
+  __syncthreads();
+  sink_flush(p, sm, cta_group, tid, K1_THREADS);
+}
+
 // ------------------------------------------------------------------------------------------------ K1 (counts entry)
 constexpr int K1C_THREADS = 256;
 __global__ void __launch_bounds__(K1C_THREADS) k1_counts(const __grid_constant__ KeyParams p) {

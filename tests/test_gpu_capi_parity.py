@@ -326,6 +326,26 @@ def test_panel_beyond_shared_memory_scorer_limits(T, h):
     compare_scan(T, res, exp)
 
 
+def test_rows_wider_than_one_ring_stage(T, h):
+    """More than 4096 samples per SNP: K1 streams each 32-SNP block in 64-word segments (k1_genotypes_wide)."""
+    rng = np.random.default_rng(77)
+    n1, n2, S = 2600, 1700, 2500
+    G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 2, 200000)
+    assert (w1 + w2) * 128 > 32 * 1024
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(GOLDEN), "..", "oracle")])
+    import sfs_oracle_c as OC
+    cnt = OC.decode(G, S, w1, w2, n1, n2, 4)
+    h.set_panel(n1, n2, True)
+    h.load_genotypes(G, S, w1, w2, n1, n2, pos, off)
+    h.background(T.BG_GENOME)
+    e2, e1, e1b = O.dense_spectra(cnt, n1, n2)
+    s2, s1a, s1b = h.get_background(0)
+    assert np.array_equal(s2.astype(np.int64), e2) and np.array_equal(s1a.astype(np.int64), e1) and np.array_equal(s1b.astype(np.int64), e1b)
+    res = h.run_bp(T.BG_PER_CHROM, 40000)
+    compare_scan(T, res, OC.scan(cnt, pos, off, n1, n2, W=40000, bg="per_chrom", nthreads=4))
+
+
 def test_capi_error_conventions(T, h):
     """Return codes + tdsfs_last_error(): call-order violations, bad arguments, small result buffers -- never a crash."""
     cnt = np.array([[2, 2, 2, 2], [3, 1, 1, 3], [4, 0, 2, 2]], dtype=np.uint16)
