@@ -91,6 +91,16 @@ struct tdsfs_ctx {
   bool float_bg = false, tables_ready = false, fin_timed = false;
   int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
   int* d_err = nullptr;
+  // peer-memory exchange of the background histogram (tdsfs_peer_*)
+  int peer_rank = -1, peer_world = 0;
+  uint32_t* peer_hist[PEER_MAX] = {};
+  unsigned long long* peer_flags[PEER_MAX] = {};
+  unsigned long long* d_peer_flags = nullptr;  // this rank's flag array
+  uint32_t* peer_exported_hist = nullptr;
+  long long peer_words = 0;
+  unsigned long long peer_epoch = 0;
+  bool peer_ready = false;
+  unsigned long long peer_pending = 0;  // epoch of the peers' "pushes landed" signal that nobody has waited for yet
   // windows / results
   long long ncand = 0, cand_cap = 0;
   std::vector<long long> cand_off_host;  // cached candidate offsets of (cand_W, cand_snp)
@@ -118,6 +128,9 @@ struct tdsfs_ctx {
   float ms[8] = {};
   long long launches = 0;
 };
+
+static void peer_unmap(tdsfs_ctx* c);
+static int peer_settle(tdsfs_ctx* c);
 
 template <typename T>
 static int dev_alloc(T** p, long long n) {
@@ -216,6 +229,8 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   if (c->pool_cnt) cudaFree(c->pool_cnt);
   if (c->pool_pos) cudaFree(c->pool_pos);
   if (c->pool_flags) cudaFree(c->pool_flags);
+  peer_unmap(c);
+  dev_free(c->d_peer_flags);
   dev_free(c->d_rec); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
   dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
   dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
@@ -256,6 +271,8 @@ extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold)
   dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum);
   c->table_groups = 0;
   dev_free(c->d_scratch);
+  peer_unmap(c);  // peers must have closed their mappings of this histogram (tdsfs_peer_close) before it is freed
+  c->peer_exported_hist = nullptr;
   dev_free(c->d_hist);
   c->hist_words = 0;
   return 0;
@@ -414,7 +431,8 @@ static int ensure_tables(tdsfs_ctx* c, int NG) {
   CKR(dev_alloc(&c->d_lb1a, (long long)NG * (c->n1 + 1)));
   CKR(dev_alloc(&c->d_lb1b, (long long)NG * (c->n2 + 1)));
   CKR(dev_alloc(&c->d_B, (long long)NG * 6));
-  CKR(dev_alloc(&c->d_Bsum, (long long)NG * 3));
+  CKR(dev_alloc(&c->d_Bsum, (long long)NG * 3 + 1));  // + the finalize kernel's CTA counter; the kernel leaves all of it zero
+  CK(cudaMemsetAsync(c->d_Bsum, 0, (size_t)(NG * 3 + 1) * 8, c->stream));
   c->table_groups = NG;
   return 0;
 }
@@ -438,11 +456,14 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   if (mode == TDSFS_BG_CHROM && (bg_chrom < 0 || bg_chrom >= c->C)) return fail(TDSFS_ERR_ARG, "background chromosome %d out of range", bg_chrom);
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  CKR(peer_settle(c));  // peers may still be pushing the previous exchange into the histogram
   CK(cudaEventRecord(c->ev[EV_BG0], st));
   const int NG = mode == TDSFS_BG_PER_CHROM ? c->C : 1;
   c->gstride = (long long)c->bins2d + c->R1 + c->R2;
   const long long words = c->gstride * NG;
   if (words > c->hist_words) {
+    peer_unmap(c);
+    c->peer_exported_hist = nullptr;
     dev_free(c->d_hist);
     CKR(dev_alloc(&c->d_hist, words));
     c->hist_words = words;
@@ -559,9 +580,140 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
 
 extern "C" int tdsfs_background_device(tdsfs_t* c, void** dev_ptr, int64_t* n_words, int32_t* n_groups) {
   if (!c || !c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  CK(cudaSetDevice(c->device));
+  CKR(peer_settle(c));
   if (dev_ptr) *dev_ptr = c->d_hist;
   if (n_words) *n_words = c->gstride * c->NG;
   if (n_groups) *n_groups = c->NG;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ peer exchange
+struct PeerBlob {  // TDSFS_PEER_BLOB_BYTES
+  cudaIpcMemHandle_t hist, flags;
+  long long words;
+  int rank, world;
+  int device, pad;
+};
+static_assert(sizeof(PeerBlob) <= TDSFS_PEER_BLOB_BYTES, "blob size");
+
+constexpr long long PEER_TIMEOUT_CYCLES = 20LL * 1000 * 1000 * 1000;  // ~10 s: a rank that never arrives flags an error instead of hanging
+
+// Something other than the finalize kernel is about to touch the histogram: wait (on the stream) for the peers' pushes.
+static int peer_settle(tdsfs_ctx* c) {
+  if (!c->peer_pending) return 0;
+  k_peer_wait<<<1, 32, 0, c->stream>>>(c->d_peer_flags, c->peer_world, c->peer_pending, c->d_err, PEER_TIMEOUT_CYCLES);
+  c->launches++;
+  c->peer_pending = 0;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static void peer_unmap(tdsfs_ctx* c) {
+  for (int r = 0; r < c->peer_world; ++r) {
+    if (r != c->peer_rank) {
+      if (c->peer_hist[r]) cudaIpcCloseMemHandle(c->peer_hist[r]);
+      if (c->peer_flags[r]) cudaIpcCloseMemHandle(c->peer_flags[r]);
+    }
+    c->peer_hist[r] = nullptr;
+    c->peer_flags[r] = nullptr;
+  }
+  c->peer_ready = false;
+  c->peer_pending = 0;
+}
+
+extern "C" int tdsfs_peer_export(tdsfs_t* c, int32_t rank, int32_t world, void* blob) {
+  if (!c || !blob) return fail(TDSFS_ERR_ARG, "NULL argument");
+  if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail(TDSFS_ERR_ARG, "rank %d / world %d out of range (max %d)", rank, world, PEER_MAX);
+  if (!c->keys_ready || !c->d_hist) return fail(TDSFS_ERR_STATE, "tdsfs_background first (the histogram must exist)");
+  if (c->NG != 1) return fail(TDSFS_ERR_STATE, "the peer exchange needs a single background group (TDSFS_BG_GENOME / _CHROM)");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  peer_unmap(c);
+  if (!c->d_peer_flags) CKR(dev_alloc(&c->d_peer_flags, PEER_MAX + 1));  // flags, then the reduce kernel's CTA counter
+  CK(cudaMemset(c->d_peer_flags, 0, (PEER_MAX + 1) * sizeof(unsigned long long)));
+  c->peer_pending = 0;
+  c->peer_epoch = 0;
+  c->peer_rank = rank;
+  c->peer_world = world;
+  c->peer_words = c->gstride;
+  c->peer_exported_hist = c->d_hist;
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  CK(cudaIpcGetMemHandle(&b.hist, c->d_hist));
+  CK(cudaIpcGetMemHandle(&b.flags, c->d_peer_flags));
+  b.words = c->peer_words; b.rank = rank; b.world = world; b.device = c->device;
+  memset(blob, 0, TDSFS_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return 0;
+}
+
+extern "C" int tdsfs_peer_import(tdsfs_t* c, const void* blobs) {
+  if (!c || !blobs) return fail(TDSFS_ERR_ARG, "NULL argument");
+  if (c->peer_world < 1 || !c->peer_exported_hist) return fail(TDSFS_ERR_STATE, "tdsfs_peer_export first");
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->peer_world; ++r) {
+    PeerBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)r * TDSFS_PEER_BLOB_BYTES, sizeof b);
+    if (b.rank != r || b.world != c->peer_world) { peer_unmap(c); return fail(TDSFS_ERR_ARG, "blob %d is from rank %d of %d", r, b.rank, b.world); }
+    if (b.words != c->peer_words) { peer_unmap(c); return fail(TDSFS_ERR_ARG, "rank %d holds a histogram of %lld words, this rank %lld: panels differ", r, b.words, c->peer_words); }
+    if (r == c->peer_rank) {
+      c->peer_hist[r] = c->d_hist;
+      c->peer_flags[r] = c->d_peer_flags;
+      continue;
+    }
+    void *ph = nullptr, *pf = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ph, b.hist, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      if (ph) cudaIpcCloseMemHandle(ph);
+      peer_unmap(c);
+      cudaGetLastError();
+      return fail(TDSFS_ERR_CUDA, "cannot map the histogram of rank %d (device %d): %s", r, b.device, cudaGetErrorString(e));
+    }
+    c->peer_hist[r] = (uint32_t*)ph;
+    c->peer_flags[r] = (unsigned long long*)pf;
+  }
+  c->peer_ready = true;
+  return 0;
+}
+
+extern "C" int tdsfs_peer_allreduce_background(tdsfs_t* c) {
+  if (!c || !c->peer_ready) return fail(TDSFS_ERR_STATE, "tdsfs_peer_export / tdsfs_peer_import first");
+  if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (c->d_hist != c->peer_exported_hist || c->NG != 1 || c->gstride != c->peer_words)
+    return fail(TDSFS_ERR_STATE, "the histogram changed since tdsfs_peer_export (panel or background mode): export again");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  PeerParams p;
+  for (int r = 0; r < PEER_MAX; ++r) { p.hist[r] = c->peer_hist[r]; p.flags[r] = c->peer_flags[r]; }
+  p.rank = c->peer_rank; p.world = c->peer_world; p.words = c->peer_words; p.err = c->d_err;
+  p.timeout_cycles = PEER_TIMEOUT_CYCLES;
+  // one launch: barrier (every rank's count kernel has finished) -> pull / sum / push slice `rank` -> signal; the
+  // wait for everybody's signal is the head of tdsfs_finalize_background's kernel (or peer_settle)
+  CKR(peer_settle(c));
+  p.epoch = c->peer_epoch + 1;
+  c->peer_epoch += 2;
+  p.ticket = reinterpret_cast<unsigned int*>(c->d_peer_flags + PEER_MAX);
+  const long long n4 = p.words / 4 / p.world + 1;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)c->sm_count));
+  k_peer_reduce<<<grid, 256, 0, st>>>(p);
+  c->launches += 1;
+  c->peer_pending = c->peer_epoch;
+  CK(cudaGetLastError());
+  c->tables_ready = false;
+  return finish(c);
+}
+
+extern "C" int tdsfs_peer_close(tdsfs_t* c) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CKR(peer_settle(c));
+  CK(cudaStreamSynchronize(c->stream));
+  peer_unmap(c);
+  c->peer_exported_hist = nullptr;
+  c->peer_world = 0;
+  c->peer_rank = -1;
   return 0;
 }
 
@@ -569,6 +721,7 @@ extern "C" int tdsfs_get_background(tdsfs_t* c, int32_t group, uint64_t* s2, uin
   if (!c || !c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
   if (group < 0 || group >= c->NG) return fail(TDSFS_ERR_ARG, "group %d out of range", group);
   CK(cudaSetDevice(c->device));
+  CKR(peer_settle(c));
   std::vector<uint32_t> h((size_t)c->gstride);
   CK(cudaMemcpyAsync(h.data(), c->d_hist + (long long)group * c->gstride, (size_t)c->gstride * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -618,14 +771,18 @@ extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
   cudaStream_t st = c->stream;
   CK(cudaEventRecord(c->ev[EV_FIN0], st));
   CKR(ensure_tables(c, c->NG));
-  CK(cudaMemsetAsync(c->d_Bsum, 0, (size_t)c->NG * 3 * 8, st));
   FinParams f;
+  memset(&f, 0, sizeof f);
   f.hist = c->d_hist; f.gstride = c->gstride; f.NG = c->NG; f.bins2d = c->bins2d; f.R1 = c->R1; f.R2 = c->R2;
-  f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum;
+  f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum; f.B = c->d_B;
+  if (c->peer_pending) {  // the kernel itself waits for the peers' pushes into this rank's histogram
+    f.wait_flags = c->d_peer_flags; f.wait_n = c->peer_world; f.wait_epoch = c->peer_pending; f.err = c->d_err;
+    f.timeout_cycles = PEER_TIMEOUT_CYCLES;
+    c->peer_pending = 0;
+  }
   dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 4, (c->bins2d + 255) / 256)), (unsigned)c->NG);
   k_finalize_counts<<<grid, 256, 0, st>>>(f);
-  k_u64_to_double<<<(c->NG * 3 + 255) / 256, 256, 0, st>>>(c->d_Bsum, c->d_B, c->NG);
-  c->launches += 2;
+  c->launches += 1;
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[EV_FIN1], st));
   c->tables_ready = true;
@@ -837,6 +994,7 @@ extern "C" int tdsfs_check(tdsfs_t* c) {
   CK(cudaStreamSynchronize(c->stream));
   int err = 0;
   CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
+  if (err & 4) return fail(TDSFS_ERR_CUDA, "peer exchange: a rank did not reach the barrier in time");
   if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
   return 0;
 }

@@ -532,6 +532,99 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes_wide(const __grid_
   sink_flush(p, sm, cta_group, tid, K1_THREADS);
 }
 
+// ------------------------------------------------------------------------------------------------ peer exchange
+// In-place all-reduce (sum) of the packed background histogram over the GPUs of one NVSwitch node, through peer memory
+// (CUDA IPC mappings of every rank's histogram): rank r pulls slice r of every rank, sums it and pushes the sum back
+// into slice r of every rank.  Ranks meet at a flag barrier before (all count kernels finished) and after (all pushes
+// landed).  flags[q][r] on rank q holds the last epoch rank r signalled.
+constexpr int PEER_MAX = 16;
+struct PeerParams {
+  uint32_t* hist[PEER_MAX];
+  unsigned long long* flags[PEER_MAX];
+  int rank, world;
+  long long words;
+  unsigned long long epoch;  // barrier 1 = epoch, barrier 2 = epoch + 1
+  int* err;
+  long long timeout_cycles;
+  unsigned int* ticket;      // CTA arrival counter of k_peer_reduce (reset by its last CTA)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// spin until the flag (in THIS rank's memory, written by a peer) reaches `epoch`; a peer that never arrives flags an error
+__device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsigned long long epoch, int* err, long long timeout_cycles) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < epoch) {
+    if (clock64() - t0 > timeout_cycles) {
+      atomicOr(err, 4);
+      break;
+    }
+  }
+}
+
+// wait-only barrier (used when something other than the finalize kernel consumes the reduced histogram)
+__global__ void k_peer_wait(const unsigned long long* flags, int world, unsigned long long epoch, int* err, long long timeout_cycles) {
+  if ((int)threadIdx.x < world) peer_wait(flags + threadIdx.x, epoch, err, timeout_cycles);
+}
+
+// One launch per rank: [barrier 1: signal "my count kernel is done" (block 0), wait for every rank's signal (all blocks)]
+// -> pull slice `rank` of every histogram, sum, push the sum into every histogram -> [signal "my pushes have landed"
+// (last block)].  The matching wait is at the head of the consumer (k_finalize_counts / k_peer_wait).
+__global__ void __launch_bounds__(256) k_peer_reduce(const __grid_constant__ PeerParams p) {
+  __shared__ int s_last;
+  if ((int)threadIdx.x < p.world) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);
+    }
+    peer_wait(p.flags[p.rank] + threadIdx.x, p.epoch, p.err, p.timeout_cycles);
+  }
+  __syncthreads();
+  const long long n4 = p.words / 4;
+  const long long lo = n4 * p.rank / p.world, hi = n4 * (p.rank + 1) / p.world;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < p.world) v[r] = __ldcg(reinterpret_cast<const uint4*>(p.hist[r]) + i);
+    uint4 s = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < p.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    for (int r = 8; r < p.world; ++r) {
+      const uint4 t = __ldcg(reinterpret_cast<const uint4*>(p.hist[r]) + i);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    for (int r = 0; r < p.world; ++r) __stcg(reinterpret_cast<uint4*>(p.hist[r]) + i, s);
+  }
+  // the last (words % 4) words: one thread of the last rank
+  if (p.rank == p.world - 1 && blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long w = n4 * 4; w < p.words; ++w) {
+      uint32_t s = 0;
+      for (int r = 0; r < p.world; ++r) s += __ldcg(p.hist[r] + w);
+      for (int r = 0; r < p.world; ++r) __stcg(p.hist[r] + w, s);
+    }
+  // every thread's pushes are ordered before the CTA's ticket; the last CTA tells every rank that this rank is done
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    if ((int)threadIdx.x < p.world) {
+      __threadfence_system();
+      st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch + 1);
+    }
+    if (threadIdx.x == 0) *p.ticket = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1 (counts entry)
 constexpr int K1C_THREADS = 256;
 __global__ void __launch_bounds__(K1C_THREADS) k1_counts(const __grid_constant__ KeyParams p) {
@@ -577,12 +670,24 @@ struct FinParams {
   double* lb2;   // [NG][bins2d]
   double* lb1a;  // [NG][n1+1]
   double* lb1b;  // [NG][n2+1]
-  unsigned long long* Bsum;  // [NG][3] interior totals
+  unsigned long long* Bsum;  // [NG][3] interior totals, then one word used as the CTA arrival counter; zero between launches
+  double* B;                 // [NG][6] = B (2D, 1D pop1, 1D pop2) then ln B
+  // multi-GPU: wait until every rank's k_peer_reduce has pushed its slice (flags in this rank's memory)
+  const unsigned long long* wait_flags;
+  int wait_n;
+  unsigned long long wait_epoch;
+  int* err;
+  long long timeout_cycles;
 };
 
 __device__ __forceinline__ double ln_count(unsigned long long v) { return v ? log((double)v) : -INFINITY; }
 
 __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__ FinParams p) {
+  __shared__ int s_last;
+  if (p.wait_n) {
+    if ((int)threadIdx.x < p.wait_n) peer_wait(p.wait_flags + threadIdx.x, p.wait_epoch, p.err, p.timeout_cycles);
+    __syncthreads();
+  }
   const int g = blockIdx.y;
   const uint32_t* h = p.hist + (long long)g * p.gstride;
   unsigned long long local = 0;
@@ -609,15 +714,20 @@ __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__
       if ((threadIdx.x & 31) == 0 && loc) atomicAdd(p.Bsum + g * 3 + 1 + pop, loc);
     }
   }
-}
-
-// interior totals -> table [group][6] = B (2D, 1D pop1, 1D pop2) then ln B
-__global__ void k_u64_to_double(const unsigned long long* in, double* out, int ngroups) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ngroups * 3) {
-    const double b = (double)in[i];
-    out[(i / 3) * 6 + i % 3] = b;
-    out[(i / 3) * 6 + 3 + i % 3] = b > 0.0 ? log(b) : -INFINITY;
+  // the last CTA to arrive turns the interior totals into the table [group][6] = B then ln B, and re-zeroes the sums
+  __threadfence();
+  __syncthreads();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(p.Bsum + (long long)p.NG * 3);
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < p.NG * 3; i += blockDim.x) {
+      const double b = (double)atomicExch(p.Bsum + i, 0ull);
+      p.B[(i / 3) * 6 + i % 3] = b;
+      p.B[(i / 3) * 6 + 3 + i % 3] = b > 0.0 ? log(b) : -INFINITY;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
   }
 }
 

@@ -20,9 +20,12 @@ EXPORTS = [
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
-    "tdsfs_poisson_score",
+    "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_close",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_version",
 ]
+
+
+PEER_BLOB_BYTES = 192  # TDSFS_PEER_BLOB_BYTES
 
 
 class TdsfsError(RuntimeError):
@@ -156,6 +159,22 @@ class Handle:
         p, n, g = C.c_void_p(), C.c_int64(), C.c_int32()
         self._check(self._L.tdsfs_background_device(self._h, C.byref(p), C.byref(n), C.byref(g)))
         return p.value, n.value, g.value
+
+    # ---- peer-memory exchange of the background (multi-GPU)
+    def peer_export(self, rank, world):
+        blob = C.create_string_buffer(PEER_BLOB_BYTES)
+        self._check(self._L.tdsfs_peer_export(self._h, C.c_int32(rank), C.c_int32(world), blob))
+        return blob.raw
+
+    def peer_import(self, blobs):
+        data = b"".join(blobs)
+        self._check(self._L.tdsfs_peer_import(self._h, C.c_char_p(data)))
+
+    def peer_allreduce_background(self):
+        self._check(self._L.tdsfs_peer_allreduce_background(self._h))
+
+    def peer_close(self):
+        self._check(self._L.tdsfs_peer_close(self._h))
 
     def get_background(self, group=0):
         R1, R2 = 2 * self.n1 + 1, 2 * self.n2 + 1

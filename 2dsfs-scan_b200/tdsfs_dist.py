@@ -52,6 +52,43 @@ def allreduce_background(hist, group=None):
     return hist
 
 
+def peer_setup(handle, group=None):
+    """Map every rank's background histogram into every other rank (CUDA IPC over NVLink) for
+    handle.peer_allreduce_background().  Collective; the handle must hold its shard and tdsfs_background must have
+    run once (single-group mode).  Returns False, leaving the NCCL path in use, when the mapping is not possible."""
+    import torch.distributed as dist
+    import tdsfs_capi as T
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    try:
+        blob = handle.peer_export(rank, world)
+    except T.TdsfsError:
+        blob = None
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob, group=group)
+    ok = all(b is not None for b in blobs)
+    if ok:
+        try:
+            handle.peer_import(blobs)
+        except T.TdsfsError:
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)  # also the host barrier: every rank has mapped before anyone signals
+    if not all(flags):
+        handle.peer_close()
+        return False
+    return True
+
+
+def peer_teardown(handle, group=None):
+    """Collective: unmap the peers' histograms before any rank frees or re-shapes its own."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    handle.peer_close()
+    dist.barrier(group=group)
+
+
 def gather_results(local, chrom_base, group=None):
     """Concatenate per-rank result arrays in rank order (== the reference's sorted window order, because ranks own
     contiguous chromosome ranges).  local: dict name -> numpy array; chrom_base: global index of this rank's first chromosome."""
@@ -66,12 +103,16 @@ def gather_results(local, chrom_base, group=None):
     return {k: np.concatenate([p[k] for p in parts]) for k in local}
 
 
-def sharded_scan_bp(handle, window_bp, bg_mode, device, group=None, chrom_base=0):
-    """background -> (all-reduce) -> finalize -> scan -> gather, for a handle that already holds this rank's shard."""
+def sharded_scan_bp(handle, window_bp, bg_mode, device, group=None, chrom_base=0, peer=False):
+    """background -> (all-reduce) -> finalize -> scan -> gather, for a handle that already holds this rank's shard.
+    peer=True: the all-reduce is the library's own peer-memory kernel (after peer_setup) instead of NCCL."""
     import tdsfs_capi as T
     handle.plan(window_bp)  # window boundaries on a side stream: overlaps the count kernel and the all-reduce
     handle.background(bg_mode)
     if bg_mode in (T.BG_GENOME, T.BG_CHROM):
-        allreduce_background(background_tensor(handle, device), group)
+        if peer:
+            handle.peer_allreduce_background()
+        else:
+            allreduce_background(background_tensor(handle, device), group)
     handle.finalize_background()
     return gather_results(handle.scan(window_bp), chrom_base, group)

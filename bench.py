@@ -290,12 +290,21 @@ def run_b200(args, cfg):
             hist_cache[ptr] = torch.as_tensor(_DevBuf(ptr, n), device=dev)
         return hist_cache[ptr]
 
+    peer = {"on": False}
+
+    def exchange():
+        """Sum the background histogram over ranks in place: the library's peer-memory kernel, else NCCL."""
+        if peer["on"]:
+            h.peer_allreduce_background()
+        else:
+            dist.all_reduce(hist_tensor())
+
     def device_step():
         """K1 (+ all-reduce of the background) + finalize + K2 + K3/K4, all enqueued on one stream, no host sync."""
         h.plan(W)                  # K2 on a side stream: overlaps K1 and the all-reduce
         h.background(T.BG_GENOME)
         if world > 1:
-            dist.all_reduce(hist_tensor())
+            exchange()
         h.finalize_background()
         h.scan(W, fetch=False)
 
@@ -310,6 +319,10 @@ def run_b200(args, cfg):
 
     # ---- (A) device-resident throughput
     h.load_genotypes(G, S_local, w1, w2, n1, n2, pos_dev, off)
+    if world > 1 and args.exchange == "peer":
+        from tdsfs_dist import peer_setup
+        h.background(T.BG_GENOME)  # allocates the histogram that the peers map
+        peer["on"] = peer_setup(h)
     h.set_sync(False)
     launches0 = h.launch_count()
     for _ in range(max(args.warmup, 3)):
@@ -341,7 +354,7 @@ def run_b200(args, cfg):
         h.plan(W)
         h.background(T.BG_GENOME)
         if world > 1:
-            dist.all_reduce(hist_tensor())
+            exchange()
             torch.cuda.synchronize()
         h.finalize_background()
         h.scan(W, fetch=False)
@@ -369,7 +382,7 @@ def run_b200(args, cfg):
             if world > 1:
                 h.plan(W)
                 h.background(T.BG_GENOME)
-                dist.all_reduce(hist_tensor())
+                exchange()
                 torch.cuda.synchronize()
                 h.finalize_background()
                 return h.scan(W, fetch=True)
@@ -397,6 +410,9 @@ def run_b200(args, cfg):
                "api": "tdsfs_load_genotypes(host) + tdsfs_run_bp(host results) via ctypes",
                "note": "per-rank bytes; PCIe host->device copy of the 2-bit matrix dominates"}
     sampler.stop()
+    if peer["on"]:
+        from tdsfs_dist import peer_teardown
+        peer_teardown(h)
 
     if rank != 0:
         if world > 1:
@@ -437,7 +453,8 @@ def run_b200(args, cfg):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 popcount/histograms + f64 likelihoods", "data": "synthetic",
             "config": {"workload": cfg["name"], "S": S_total, "n1": n1, "n2": n2, "window_bp": W, "windows": n_windows_total,
                        "chromosomes": cfg["C"], "sharding": f"contiguous chromosome ranges over {world} rank(s)", "background": "genome-wide"
-                       + (", all-reduced (NCCL, uint32 sum)" if world > 1 else ""), "row_bytes": RW * 4,
+                       + ((", all-reduced in place by the library's peer-memory kernel (CUDA IPC over NVLink, uint32 sum)" if peer["on"]
+                          else ", all-reduced (NCCL, uint32 sum)") if world > 1 else ""), "row_bytes": RW * 4,
                        "l2": "inputs (per-rank genotype matrix %.1f GB) larger than L2" % (S_local * RW * 4 / 1e9)},
             "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary(windows)}
@@ -454,6 +471,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config5", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: background all-reduce through the library's peer-memory kernel (default) or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -127,6 +127,26 @@ int tdsfs_background(tdsfs_t* ctx, int32_t mode, int32_t bg_chrom, int64_t bg_po
  * before tdsfs_finalize_background.  n_words = total uint32 words. */
 int tdsfs_background_device(tdsfs_t* ctx, void** dev_ptr, int64_t* n_words, int32_t* n_groups);
 
+/* ---- peer-memory exchange of the background (multi-GPU, one process per GPU on one NVLink/NVSwitch node) -----
+ * The genome-wide background of a chromosome-sharded scan is the SUM of the ranks' histograms; the reference
+ * computes it in one process (calculate_2d_sfs on the whole data_dict, :809-825), so this step has no reference
+ * counterpart.  Instead of a library all-reduce, every rank maps every other rank's histogram (CUDA IPC) and one
+ * kernel per rank pulls its slice of all histograms over NVLink, sums it and pushes the sum back into all of them,
+ * between two flag barriers in peer memory.  Protocol, collectively on all ranks:
+ *   tdsfs_background(...)                       once, so that the histogram exists (single group: GENOME / CHROM)
+ *   tdsfs_peer_export(ctx, rank, world, blob)   fills blob[TDSFS_PEER_BLOB_BYTES]; exchange blobs out of band
+ *   tdsfs_peer_import(ctx, blobs)               blobs = world x TDSFS_PEER_BLOB_BYTES in rank order
+ *   per scan: tdsfs_background -> tdsfs_peer_allreduce_background -> tdsfs_finalize_background -> tdsfs_scan_*
+ *   tdsfs_peer_close(ctx)                       on every rank BEFORE any rank changes its panel or is destroyed
+ * tdsfs_peer_allreduce_background is asynchronous on the handle's stream; all ranks must call it the same number
+ * of times.  A rank that never arrives makes the others flag TDSFS_ERR_CUDA (tdsfs_check) after ~10 s, not hang. */
+#define TDSFS_PEER_BLOB_BYTES 192
+#define TDSFS_PEER_MAX_RANKS 16
+int tdsfs_peer_export(tdsfs_t* ctx, int32_t rank, int32_t world, void* blob);
+int tdsfs_peer_import(tdsfs_t* ctx, const void* blobs);
+int tdsfs_peer_allreduce_background(tdsfs_t* ctx);
+int tdsfs_peer_close(tdsfs_t* ctx);
+
 /* Copy one group's integer spectra to the host: sfs2d[(2n1+1)*(2n2+1)] row-major (i,j) = calculate_2d_sfs,
  * sfs1d_p1[2n1+1] / sfs1d_p2[2n2+1] = calculate_1d_sfs (unfolded).  Any pointer may be NULL. */
 int tdsfs_get_background(tdsfs_t* ctx, int32_t group, uint64_t* sfs2d, uint64_t* sfs1d_p1, uint64_t* sfs1d_p2);

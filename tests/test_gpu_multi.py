@@ -1,5 +1,6 @@
-"""2-GPU parity: a scan sharded by contiguous chromosome ranges with the background all-reduced over NCCL equals the
-single-GPU scan (integers bit for bit, fp64 to 1e-12).  Skipped on boxes with fewer than two GPUs."""
+"""2-GPU parity: a scan sharded by contiguous chromosome ranges with the background all-reduced (NCCL, and the library's
+own peer-memory kernel) equals the single-GPU scan (integers bit for bit, fp64 to 1e-12).  Skipped on boxes with
+fewer than two GPUs."""
 import os
 import socket
 import sys
@@ -30,13 +31,13 @@ def _panel():
     return n1, n2, sizes, c1, c2, pos, pack_codes
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, peer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, os.path.join(ROOT, "2dsfs-scan_b200"))
     import torch
     import torch.distributed as dist
     import tdsfs_capi as T
-    from tdsfs_dist import shard_chromosomes, sharded_scan_bp
+    from tdsfs_dist import shard_chromosomes, sharded_scan_bp, peer_setup, peer_teardown
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     n1, n2, sizes, c1, c2, pos, pack_codes = _panel()
@@ -47,13 +48,22 @@ def _worker(rank, world, port, out):
     h = T.Handle(rank)
     h.set_panel(n1, n2, True)
     h.load_genotypes(G, int(b - a), w1, w2, n1, n2, pos[a:b], off[lo:hi + 1] - off[lo])
-    res = sharded_scan_bp(h, 20000, T.BG_GENOME, torch.device("cuda", rank), chrom_base=lo)
+    if peer:
+        h.background(T.BG_GENOME)  # the histogram must exist before it can be exported
+        assert peer_setup(h), "CUDA IPC mapping of the peers' histograms failed"
+        for _ in range(3):         # repeated scans: barrier epochs advance, the histogram is re-zeroed every time
+            res = sharded_scan_bp(h, 20000, T.BG_GENOME, torch.device("cuda", rank), chrom_base=lo, peer=True)
+        h._check(h._L.tdsfs_check(h._h))
+        peer_teardown(h)
+    else:
+        res = sharded_scan_bp(h, 20000, T.BG_GENOME, torch.device("cuda", rank), chrom_base=lo)
     if rank == 0:
         out["res"] = {k: v.tolist() for k, v in res.items()}
     dist.destroy_process_group()
 
 
-def test_sharded_scan_equals_single_gpu():
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer-memory"])
+def test_sharded_scan_equals_single_gpu(peer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -62,7 +72,7 @@ def test_sharded_scan_equals_single_gpu():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, peer), nprocs=2, join=True)
     n1, n2, sizes, c1, c2, pos, pack_codes = _panel()
     off = np.concatenate([[0], np.cumsum(sizes)])
     G, w1, w2 = pack_codes(c1, c2)
