@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libtdsfs.so")
 
 BG_NONE, BG_PER_CHROM, BG_GENOME, BG_CHROM = 0, 1, 2, 3
 F_T2D_NONE, F_T1D_P1_NONE, F_T1D_P2_NONE, F_EMPTY, F_SKIPPED = 1, 2, 4, 8, 16
-ERR_RANGE = 4
+ERR_ARG, ERR_CUDA, ERR_STATE, ERR_RANGE = 1, 2, 3, 4
 
 EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",

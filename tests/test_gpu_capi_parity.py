@@ -346,6 +346,46 @@ def test_rows_wider_than_one_ring_stage(T, h):
     compare_scan(T, res, OC.scan(cnt, pos, off, n1, n2, W=40000, bg="per_chrom", nthreads=4))
 
 
+def test_peer_exchange_single_rank(T, h):
+    """The peer-memory all-reduce with world = 1 (this rank maps only itself): barrier epochs, in-place reduce and the
+    finalize kernel's wait all run, and the scan equals the plain one.  Two ranks: tests/test_gpu_multi.py."""
+    rng = np.random.default_rng(31)
+    n1, n2, S = 20, 16, 9000
+    G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 3, 120000)
+    h.set_panel(n1, n2, True)
+    h.load_genotypes(G, S, w1, w2, n1, n2, pos, off)
+    plain = h.run_bp(T.BG_GENOME, 6000)
+    with pytest.raises(T.TdsfsError) as ei:       # not set up yet
+        h.peer_allreduce_background()
+    assert ei.value.code == T.ERR_STATE
+    h.background(T.BG_GENOME)
+    blob = h.peer_export(0, 1)
+    assert len(blob) == T.PEER_BLOB_BYTES
+    with pytest.raises(T.TdsfsError):             # blob of the wrong rank
+        h.peer_import([b"\x01" * T.PEER_BLOB_BYTES])
+    blob = h.peer_export(0, 1)
+    h.peer_import([blob])
+    for _ in range(3):
+        h.background(T.BG_GENOME)
+        h.peer_allreduce_background()
+        s2, s1a, s1b = h.get_background(0)        # settles the pending wait without finalize
+        h.peer_allreduce_background()             # sum over one rank: unchanged
+        h.finalize_background()
+        res = h.scan(6000)
+    for k in plain:
+        if plain[k].dtype == np.float64:
+            assert np.allclose(res[k], plain[k], rtol=1e-12, atol=1e-12, equal_nan=True), k
+        else:
+            assert np.array_equal(res[k], plain[k]), k
+    h.background(T.BG_PER_CHROM)                  # several groups: the exchange refuses
+    with pytest.raises(T.TdsfsError) as ei:
+        h.peer_allreduce_background()
+    assert ei.value.code == T.ERR_STATE
+    h.peer_close()
+    with pytest.raises(T.TdsfsError):
+        h.peer_allreduce_background()
+
+
 def test_capi_error_conventions(T, h):
     """Return codes + tdsfs_last_error(): call-order violations, bad arguments, small result buffers -- never a crash."""
     cnt = np.array([[2, 2, 2, 2], [3, 1, 1, 3], [4, 0, 2, 2]], dtype=np.uint16)
