@@ -978,38 +978,70 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
       }
     }
     gsync();
-    // ---- pass 2: walk the table (shared-memory atomics are the scarce resource here: no occupied-slot list is kept)
+    // ---- pass 2: walk the table (shared-memory atomics are the scarce resource here: no occupied-slot list is kept).
+    // U slots per thread are read first and all their ln b / ln x gathers issued together, branch-free: the gathers
+    // come from L2 (~700 cycles), so their number in flight - not their count - sets the time of this pass.
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     uint32_t N2 = 0, N1a = 0, N1b = 0;
-#pragma unroll 2
-    for (int j = tg; j < HASH_SLOTS; j += GT) {
-      const uint32_t e = tab[j];
-      if (e != EMPTY_KEY) {
-        tab[j] = EMPTY_KEY;
-        const uint32_t x = e & ((1u << KEY_SHIFT) - 1);
-        acc_bin(a2, x, p.lnI, lb2, (int)(e >> KEY_SHIFT));
-        N2 += x;
+    {
+      constexpr int PER = HASH_SLOTS / GT;       // slots per thread
+      constexpr int U = PER < 8 ? PER : 8;
+#pragma unroll 1
+      for (int j0 = tg; j0 < HASH_SLOTS; j0 += U * GT) {
+        uint32_t e[U];
+        double lbv[U], lnx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = tab[j0 + u * GT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool occ = e[u] != EMPTY_KEY;
+          const uint32_t x = occ ? (e[u] & ((1u << KEY_SHIFT) - 1)) : 0u;
+          lbv[u] = occ ? __ldg(lb2 + (e[u] >> KEY_SHIFT)) : 0.0;
+          lnx[u] = x > 1 ? __ldg(p.lnI + x) : 0.0;  // ln 1 = 0: singletons (most occupied slots) need no table read
+          e[u] = x;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) tab[j0 + u * GT] = EMPTY_KEY;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (e[u]) a2 = fma((double)e[u], lnx[u] - lbv[u], a2);
+          N2 += e[u];
+        }
       }
     }
-    // ---- pass 3: folded 1D bins (two per word)
-    for (int w = tg; w < nw1; w += GT) {
-      const uint32_t v = h1a[w];
-      if (v) {
-        h1a[w] = 0;
-        acc_bin(a1a, v & 0xFFFF, p.lnI, lb1a, 2 * w);
-        acc_bin(a1a, v >> 16, p.lnI, lb1a, 2 * w + 1);
-        N1a += (v & 0xFFFF) + (v >> 16);
+    // ---- pass 3: folded 1D bins (two per word), four words = eight bins per thread in flight
+    auto walk1d = [&](uint32_t* h1, int nw, const double* lb, double& acc, uint32_t& N) {
+      constexpr int U = 4;
+#pragma unroll 1
+      for (int w0 = tg; w0 < nw; w0 += U * GT) {
+        uint32_t v[U];
+        double lbv[2 * U], lnx[2 * U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * GT;
+          v[u] = w < nw ? h1[w] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * GT;
+          const uint32_t x0 = v[u] & 0xFFFF, x1 = v[u] >> 16;
+          lbv[2 * u] = x0 ? __ldg(lb + 2 * w) : 0.0;
+          lbv[2 * u + 1] = x1 ? __ldg(lb + 2 * w + 1) : 0.0;
+          lnx[2 * u] = x0 > 1 ? __ldg(p.lnI + x0) : 0.0;
+          lnx[2 * u + 1] = x1 > 1 ? __ldg(p.lnI + x1) : 0.0;
+          if (v[u]) h1[w] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t x0 = v[u] & 0xFFFF, x1 = v[u] >> 16;
+          if (x0) acc = fma((double)x0, lnx[2 * u] - lbv[2 * u], acc);
+          if (x1) acc = fma((double)x1, lnx[2 * u + 1] - lbv[2 * u + 1], acc);
+          N += x0 + x1;
+        }
       }
-    }
-    for (int w = tg; w < nw2; w += GT) {
-      const uint32_t v = h1b[w];
-      if (v) {
-        h1b[w] = 0;
-        acc_bin(a1b, v & 0xFFFF, p.lnI, lb1b, 2 * w);
-        acc_bin(a1b, v >> 16, p.lnI, lb1b, 2 * w + 1);
-        N1b += (v & 0xFFFF) + (v >> 16);
-      }
-    }
+    };
+    walk1d(h1a, nw1, lb1a, a1a, N1a);
+    walk1d(h1b, nw2, lb1b, a1b, N1b);
     // ---- reduce: warp level, then across the group's warps through shared memory
     // N2 | N1a << 10 | N1b << 20 : every total is <= WCAP < 1024
     uint32_t nn = __reduce_add_sync(0xffffffffu, N2 | (N1a << 10) | (N1b << 20));
