@@ -906,8 +906,9 @@ __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
   return n1 <= 32767 && n2 <= 32767 && bins2d < (1 << (32 - KEY_SHIFT)) - 1;
 }
 
-__device__ __forceinline__ void acc_bin(double& acc, uint32_t x, const double* lnI, const double* lb, int k) {
-  if (x) acc = fma((double)x, __ldg(lnI + x) - __ldg(lb + k), acc);  // (branch-free: a divergent x == 1 path doubles the gathers)
+// exact uint32 -> double on the integer + fp64 pipes (I2F.F64 runs on the quarter-rate conversion unit)
+__device__ __forceinline__ double u32_to_double(uint32_t x) {
+  return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;  // 2^52 + x, minus 2^52
 }
 
 template <int G>
@@ -946,18 +947,19 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
 
-    // ---- pass 1: up to four records per thread in flight (the loads are independent of the table work)
+    // ---- pass 1: up to Q records per thread in flight (the loads are independent of the table work)
+    constexpr int Q = G == 1 ? 8 : 4;
     int count = 0, nall = 0;
-    for (int base = 0; base < cnt; base += 4 * GT) {
-      uint2 r[4];
+    for (int base = 0; base < cnt; base += Q * GT) {
+      uint2 r[Q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const int i = base + q * GT + tg;
         r[q] = i < cnt ? __ldcs(p.rec + lo + i) : make_uint2(0u, 0u);  // streamed once: keep the ln b table in L2
         if (has_flags && i < cnt) count += (__ldg(p.flags + lo + i) >> 1) & 1;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const uint32_t k = r[q].x;
         if (p.snp_mode) nall += k != 0;
         if (k != 0 && k != last) {
@@ -1004,7 +1006,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
         for (int u = 0; u < U; ++u) tab[j0 + u * GT] = EMPTY_KEY;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (e[u]) a2 = fma((double)e[u], lnx[u] - lbv[u], a2);
+          if (e[u]) a2 = fma(u32_to_double(e[u]), lnx[u] - lbv[u], a2);
           N2 += e[u];
         }
       }
@@ -1034,8 +1036,8 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const uint32_t x0 = v[u] & 0xFFFF, x1 = v[u] >> 16;
-          if (x0) acc = fma((double)x0, lnx[2 * u] - lbv[2 * u], acc);
-          if (x1) acc = fma((double)x1, lnx[2 * u + 1] - lbv[2 * u + 1], acc);
+          if (x0) acc = fma(u32_to_double(x0), lnx[2 * u] - lbv[2 * u], acc);
+          if (x1) acc = fma(u32_to_double(x1), lnx[2 * u + 1] - lbv[2 * u + 1], acc);
           N += x0 + x1;
         }
       }
