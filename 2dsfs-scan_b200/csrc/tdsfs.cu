@@ -534,11 +534,13 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
       p.cwarps = std::min(K1_CWARPS, fit);
+      if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(p.cwarps, atoi(e)));  // tuning knob
       p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));  // `depth` stages per warp
       const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
       void (*kern)(KeyParams) = k1_genotypes<0, 0>;
       if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
       else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
+      if (getenv("TDSFS_K1_PROBE")) kern = k1_probe_ring;  // bandwidth probe, no spectra (profiling only)
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       p.interleave = (p.bg_group == nullptr) ? 1 : 0;
       if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;

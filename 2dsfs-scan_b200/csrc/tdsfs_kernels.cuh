@@ -422,26 +422,32 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
       const uint32_t* tile = reinterpret_cast<const uint32_t*>(my_stages + (size_t)slot * p.stage_bytes);
       for (int b = 0; b < nb; ++b) {
         const long long s = (blk0 + b) * BLK + lane;
+        uint32_t T1 = 0, M1 = 0, T2 = 0, M2 = 0;
         if (s < p.r1) {
           const uint32_t* rowp = tile + (size_t)b * block_words + lane;
-          uint32_t T1, M1, T2, M2;
           if (TW1 > 0 && TW1 == TW2) {
             count_two_blocks_b32<TW1>(rowp, rowp + W1 * BLK, T1, M1, T2, M2);
           } else {
             count_block_b32<TW1>(rowp, W1, T1, M1);
             count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
           }
+        }
+        if (b == nb - 1) {
+          // the stage has been read completely: refill it BEFORE the fold / record / histogram work of its last block,
+          // so that work overlaps the next load instead of delaying it
+          __syncwarp();
+          if (lane == 0) {
+            const long long nxt = i + (long long)depth * p.cwarps;
+            if (nxt < n) {
+              fence_proxy_async();  // order this warp's generic-proxy reads of the stage before the async-proxy refill
+              issue(nxt, slot);
+            }
+          }
+        }
+        if (s < p.r1) {
           const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
           const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
           sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        const long long nxt = i + (long long)depth * p.cwarps;
-        if (nxt < n) {
-          fence_proxy_async();  // order this warp's generic-proxy reads of the stage before the async-proxy refill
-          issue(nxt, slot);
         }
       }
       if (++slot == depth) { slot = 0; ph ^= 1; }
@@ -449,6 +455,59 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
   }
   __syncthreads();
   sink_flush(p, sm, cta_group, tid, K1_THREADS);
+}
+
+// Bandwidth probe (TDSFS_K1_PROBE=1, profiling only - produces no spectra): the ring traffic of k1_genotypes without the
+// counting, i.e. the ceiling of this access pattern.  Each lane folds one word per block into a checksum so the loads stay.
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_probe_ring(const __grid_constant__ KeyParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int RW = p.W1 + p.W2;
+  uint8_t* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long b0 = p.r0 / BLK, b1 = (p.r1 + BLK - 1) / BLK;
+  const long long ntiles = (b1 - b0 + p.tile_blocks - 1) / p.tile_blocks;
+  const long long t0 = p.interleave ? blockIdx.x : ntiles * blockIdx.x / gridDim.x;
+  const long long tstride = p.interleave ? gridDim.x : 1;
+  const long long n = p.interleave ? (ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0)
+                                   : ntiles * (blockIdx.x + 1) / gridDim.x - t0;
+  const long long block_words = (long long)RW * BLK;
+  const int depth = p.nstage / p.cwarps;
+  uint32_t sum = 0;
+  if (warp < p.cwarps) {
+    uint8_t* my_stages = stages + (size_t)warp * depth * p.stage_bytes;
+    uint64_t* my_full = full + warp * depth;
+    auto issue = [&](long long i, int slot) {
+      const long long blk0 = b0 + (t0 + i * tstride) * p.tile_blocks;
+      const uint32_t bytes = (uint32_t)(min((long long)p.tile_blocks, b1 - blk0) * block_words * 4);
+      mbar_arrive_expect_tx(my_full + slot, bytes);
+      bulk_g2s_stream(my_stages + (size_t)slot * p.stage_bytes, p.G + blk0 * block_words, bytes, my_full + slot);
+    };
+    if (lane == 0)
+      for (int j = 0; j < depth; ++j)
+        if (warp + (long long)j * p.cwarps < n) issue(warp + (long long)j * p.cwarps, j);
+    int slot = 0;
+    uint32_t ph = 0;
+    for (long long i = warp; i < n; i += p.cwarps) {
+      mbar_wait(my_full + slot, ph);
+      sum += reinterpret_cast<const uint32_t*>(my_stages + (size_t)slot * p.stage_bytes)[lane];
+      __syncwarp();
+      if (lane == 0) {
+        const long long nxt = i + (long long)depth * p.cwarps;
+        if (nxt < n) {
+          fence_proxy_async();
+          issue(nxt, slot);
+        }
+      }
+      if (++slot == depth) { slot = 0; ph ^= 1; }
+    }
+  }
+  if (sum == 0xFFFFFFFFu) p.hist[0] = sum;  // keeps the loads alive
 }
 
 // K1 for rows wider than one ring stage (more than 4096 samples): a 32-SNP block is streamed as segments of `seg_words`
