@@ -949,7 +949,9 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       if (const char* e = getenv("TDSFS_SCORE_G")) G = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);  // tuning knob
       while (G < SCORE_WARPS && (SCORE_WARPS / G) * gwords * 4 > 200 * 1024) G *= 2;  // fewer, wider groups for big panels
       const int smem = (SCORE_WARPS / G) * gwords * 4;
-      void (*sk)(ScoreParams) = G >= 8 ? k3_score_small<8> : (G == 4 ? k3_score_small<4> : (G == 2 ? k3_score_small<2> : k3_score_small<1>));
+      const bool extra = snp_mode || c->dFlags != nullptr;
+      void (*sk)(ScoreParams) = extra ? (G >= 8 ? k3_score_small<8, true> : (G == 4 ? k3_score_small<4, true> : (G == 2 ? k3_score_small<2, true> : k3_score_small<1, true>)))
+                                      : (G >= 8 ? k3_score_small<8, false> : (G == 4 ? k3_score_small<4, false> : (G == 2 ? k3_score_small<2, false> : k3_score_small<1, false>)));
       CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 1;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sk, SCORE_WARPS * 32, smem));

@@ -970,7 +970,15 @@ __device__ __forceinline__ double u32_to_double(uint32_t x) {
   return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;  // 2^52 + x, minus 2^52
 }
 
-template <int G>
+// predicated shared-memory reduction (no branch, no return value): bump the 16-bit half `f & 1` of word `f >> 1` when f != 0
+__device__ __forceinline__ void bump_half_if(uint32_t* h, uint32_t f) {
+  const uint32_t addr = smem_u32(h) + ((f << 1) & ~3u);
+  const uint32_t val = (f & 1u) ? 0x10000u : 1u;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.shared.add.u32 [%1], %2;\n\t}" ::"r"(f), "r"(addr), "r"(val) : "memory");
+}
+
+// EXTRA = the scan has per-SNP flags or fixed-SNP windows (extra per-record bookkeeping); false for the plain fixed-bp scan
+template <int G, bool EXTRA>
 __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p) {
   extern __shared__ __align__(16) uint32_t sm32[];
   constexpr int GT = G * 32;                 // threads per group
@@ -990,7 +998,8 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   for (int i = tg; i < nw1 + nw2; i += GT) h1a[i] = 0;
   gsync();
   const uint32_t last = (uint32_t)p.bins2d - 1;
-  const bool has_flags = p.flags != nullptr;
+  const bool has_flags = EXTRA && p.flags != nullptr;
+  const bool snp_mode = EXTRA && p.snp_mode;
 
   const long long ngroups = (long long)gridDim.x * GROUPS;
   for (long long id = (long long)blockIdx.x * GROUPS + grp; id < p.ncand; id += ngroups) {
@@ -1020,7 +1029,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const uint32_t k = r[q].x;
-        if (p.snp_mode) nall += k != 0;
+        if (snp_mode) nall += k != 0;
         if (k != 0 && k != last) {
           uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
           while (true) {  // read first: a shared-memory CAS costs about twice a load or an add
@@ -1034,8 +1043,8 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
           }
         }
         const uint32_t fa = r[q].y & 0xFFFF, fb = r[q].y >> 16;
-        if (fa) atomicAdd(h1a + (fa >> 1), 1u << (16 * (fa & 1)));
-        if (fb) atomicAdd(h1b + (fb >> 1), 1u << (16 * (fb & 1)));
+        bump_half_if(h1a, fa);
+        bump_half_if(h1b, fb);
       }
     }
     gsync();
@@ -1107,7 +1116,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     // N2 | N1a << 10 | N1b << 20 : every total is <= WCAP < 1024
     uint32_t nn = __reduce_add_sync(0xffffffffu, N2 | (N1a << 10) | (N1b << 20));
     if (has_flags) count = __reduce_add_sync(0xffffffffu, count);
-    if (p.snp_mode) nall = __reduce_add_sync(0xffffffffu, nall);
+    if (snp_mode) nall = __reduce_add_sync(0xffffffffu, nall);
     a2 = warp_sum(a2); a1a = warp_sum(a1a); a1b = warp_sum(a1b);
     if (G > 1) {
       if (lane == 0) {
