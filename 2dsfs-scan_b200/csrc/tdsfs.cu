@@ -357,8 +357,9 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
                                     const tdsfs_fixup_t* fixups, int64_t n_fixups, const uint8_t* snp_flags) {
   if (!c || !G) return fail(TDSFS_ERR_ARG, "ctx / G is NULL");
   if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
-  if (words1 < 1 || words2 < 1 || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
-    return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d)", words1, words2, ns1, ns2);
+  if (words1 < 2 || words2 < 2 || (words1 & 1) || (words2 & 1) || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
+    return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d): a population is an even number of words, 32 samples per (lo, hi) pair",
+                words1, words2, ns1, ns2);
   if (ns1 > 65535 / 2 || ns2 > 65535 / 2) return fail(TDSFS_ERR_ARG, "more than 32767 samples per population");
   CK(cudaSetDevice(c->device));
   free_data(c);
@@ -539,7 +540,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
       void (*kern)(KeyParams) = k1_genotypes<0, 0>;
       if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
-      else if (c->W1 == 13 && c->W2 == 13) kern = k1_genotypes<13, 13>;   // 200 + 200 diploids (BASELINE config 4)
+      else if (c->W1 == 14 && c->W2 == 14) kern = k1_genotypes<14, 14>;   // 200 + 200 diploids (BASELINE config 4)
       if (getenv("TDSFS_K1_PROBE")) kern = k1_probe_ring;  // bandwidth probe, no spectra (profiling only)
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       p.interleave = (p.bg_group == nullptr) ? 1 : 0;

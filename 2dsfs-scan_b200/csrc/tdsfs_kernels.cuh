@@ -150,25 +150,21 @@ struct BitCounter {
   }
 };
 
-// Two words' MISSING planes packed into one word: code 0b10 = missing -> bit (hi & ~lo).
-// wa's flags land on even bit positions, wb's on odd positions.
-__device__ __forceinline__ uint32_t pack_missing(uint32_t wa, uint32_t wb) {
-  uint32_t fa = (wa >> 1) & ~wa;  // valid at even bits
-  uint32_t fb = wb & ~(wb << 1);  // valid at odd bits
-  return (fa & 0x55555555u) | (fb & 0xAAAAAAAAu);  // one LOP3
-}
+// MISSING plane of 32 samples from their two bit-plane words: code 0b10 = missing -> hi & ~lo (one LOP3).
+__device__ __forceinline__ uint32_t missing_plane(uint32_t lo, uint32_t hi) { return hi & ~lo; }
 
 // Per-population accumulation over one row block held in shared memory.
+// Words come in (lo plane, hi plane) pairs of 32 samples.
 // alt = popcount(all bits) - #missing   (codes 00 -> 0, 01 -> 1, 11 -> 2, 10 = missing -> popcount 1, removed)
 struct PopCounts {
   BitCounter bits, miss;
   __device__ __forceinline__ void chunk4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     bits.add4(w0, w1, w2, w3);
-    miss.add2(pack_missing(w0, w1), pack_missing(w2, w3));
+    miss.add2(missing_plane(w0, w1), missing_plane(w2, w3));
   }
   __device__ __forceinline__ void chunk8(uint4 a, uint4 b) {
     bits.add8(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
-    miss.add4(pack_missing(a.x, a.y), pack_missing(a.z, a.w), pack_missing(b.x, b.y), pack_missing(b.z, b.w));
+    miss.add4(missing_plane(a.x, a.y), missing_plane(a.z, a.w), missing_plane(b.x, b.y), missing_plane(b.z, b.w));
   }
 };
 
@@ -1241,10 +1237,10 @@ __global__ void k_window_hist(const __grid_constant__ KeyParams p, int lo, int h
     } else {
       const uint32_t* row = p.G + ((s >> 5) * RW) * BLK + (s & 31);
       int T[2] = {0, 0}, M[2] = {0, 0};
-      for (int w = 0; w < RW; ++w) {
-        const uint32_t x = row[(long long)w * BLK];
-        T[w >= p.W1] += __popc(x);
-        M[w >= p.W1] += __popc((x >> 1) & ~x & 0x55555555u);
+      for (int w = 0; w < RW; w += 2) {  // (lo plane, hi plane) of 32 samples; W1 and W2 are even
+        const uint32_t l = row[(long long)w * BLK], h = row[(long long)(w + 1) * BLK];
+        T[w >= p.W1] += __popc(l) + __popc(h);
+        M[w >= p.W1] += __popc(h & ~l);
       }
       alt1 = T[0] - M[0]; alt2 = T[1] - M[1];
       ref1 = 2 * (p.ns1 - M[0]) - alt1; ref2 = 2 * (p.ns2 - M[1]) - alt2;
@@ -1324,7 +1320,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 }
 __device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
 
-// one thread per (row, word): 16 calls.  Ancestral frequency log-uniform on [1/(8n), 1-1/(8n)], per-population
+// one thread per (row, word): one bit plane of 32 calls.  Ancestral frequency log-uniform on [1/(8n), 1-1/(8n)], per-population
 // drift ~ normal approximation of Balding-Nichols with F = fst, calls Binomial(2, p), iid missing.
 __global__ void __launch_bounds__(256) k_synth(uint32_t* G, long long S, long long snp0, int W1, int W2, int ns1, int ns2,
                                                uint64_t seed, uint32_t miss_thr16, double fst) {
@@ -1352,15 +1348,16 @@ __global__ void __launch_bounds__(256) k_synth(uint32_t* G, long long S, long lo
   pp = fmin(fmax(pp, 0.0), 1.0);
   const uint32_t thr = (uint32_t)(pp * 4294967296.0 > 4294967295.0 ? 4294967295.0 : pp * 4294967296.0);
   uint32_t word = 0;
-  for (int i = 0; i < 16; ++i) {
-    const int sample = wi * 16 + i;
+  const int plane = wi & 1;  // 0: lo bits of the codes, 1: hi bits
+  for (int i = 0; i < 32; ++i) {
+    const int sample = (wi >> 1) * 32 + i;
     if (sample >= ns) break;
     const uint64_t h1 = mix64(hs ^ ((uint64_t)(pop * 1000003 + sample + 1) * 0xD6E8FEB86659FD93ULL));
     const uint64_t h2 = mix64(h1);
     const uint32_t a1 = (uint32_t)h1 < thr, a2 = (uint32_t)(h1 >> 32) < thr;
     uint32_t code = (a1 + a2 == 0) ? 0u : (a1 + a2 == 1 ? 1u : 3u);
     if ((uint32_t)(h2 & 0xFFFF) < miss_thr16) code = 2u;
-    word |= code << (2 * i);
+    word |= ((code >> plane) & 1u) << i;
   }
   G[idx] = word;
 }

@@ -110,7 +110,7 @@ void parse_line(const std::string& line, const Plan& plan, Rec& r) {
   for (int pop = 0; pop < 2; ++pop) {
     const int ns = pop ? plan.ns2 : plan.ns1;
     uint32_t* w = r.words.data() + (pop ? plan.W1 : 0);
-    for (int s = 0; s < ns; ++s) w[s >> 4] |= 2u << (2 * (s & 15));
+    for (int s = 0; s < ns; ++s) w[2 * (s >> 5) + 1] |= 1u << (s & 31);  // code 2 = (lo 0, hi 1)
   }
   const size_t ncol = std::min(plan.col_pop.size(), cols.size() - 9);
   for (size_t j = 0; j < ncol; ++j) {
@@ -131,8 +131,11 @@ void parse_line(const std::string& line, const Plan& plan, Rec& r) {
       if (ref || alt) r.fix.push_back({0, pop, ref, alt});
     }
     const int slot = plan.col_slot[j];
-    uint32_t* w = r.words.data() + (pop ? plan.W1 : 0) + (slot >> 4);
-    *w = (*w & ~(3u << (2 * (slot & 15)))) | (code << (2 * (slot & 15)));
+    // samples 32g..32g+31 of a population: word 2g = lo bits of their codes, word 2g+1 = hi bits
+    uint32_t* w = r.words.data() + (pop ? plan.W1 : 0) + 2 * (slot >> 5);
+    const uint32_t bit = 1u << (slot & 31);
+    w[0] = (w[0] & ~bit) | ((code & 1u) ? bit : 0u);
+    w[1] = (w[1] & ~bit) | ((code & 2u) ? bit : 0u);
   }
   r.ok = true;
 }
@@ -186,8 +189,8 @@ void* tdsfs_pack_vcf(const char* vcf_path, const char* popmap_path, const char* 
         plan.col_pop.push_back(pop);
         plan.col_slot.push_back(pop == 0 ? plan.ns1++ : (pop == 1 ? plan.ns2++ : 0));
       }
-      plan.W1 = std::max(1, (plan.ns1 + 15) / 16);
-      plan.W2 = std::max(1, (plan.ns2 + 15) / 16);
+      plan.W1 = 2 * std::max(1, (plan.ns1 + 31) / 32);  // a (lo plane, hi plane) word pair per 32 samples
+      plan.W2 = 2 * std::max(1, (plan.ns2 + 31) / 32);
     };
     rebuild_plan();
 

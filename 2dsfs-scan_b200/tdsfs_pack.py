@@ -1,8 +1,9 @@
 """Host-side packing of genotype calls into the 2-bit-per-call matrix the GPU consumes (K0).
 
-Per SNP: uint32 words of 16 calls (call i in bits 2i..2i+1), population-1 words then population-2 words, each
-population padded with zeros to a whole word.  Codes: 0 = 0/0, 1 = 0/1, 3 = 1/1, 2 = missing, so that
-alt = popcount(block) - #missing  and  ref = 2*(samples - #missing) - alt.
+Per SNP: the 2-bit codes of 32 samples are stored as two bit-plane words, (lo bits, hi bits), bit b = sample 32g + b of
+group g; population-1 pairs then population-2 pairs, each population padded with zeros to a whole pair.  Codes:
+0 = 0/0, 1 = 0/1, 3 = 1/1, 2 = missing, so that #missing = popcount(hi & ~lo), alt = popcount(all words) - #missing
+and ref = 2*(samples - #missing) - alt: the count kernel needs one logic op per 32 samples to find the missing calls.
 Memory layout "B32" (block-transposed): SNPs are grouped in blocks of 32; word w of SNP s is stored at uint32 index
 ((s // 32) * RW + w) * 32 + s % 32, RW = W1 + W2.  A warp therefore reads word w of 32 consecutive SNPs as one
 128-byte line, and in shared memory as one conflict-free access.  The last block is zero padded.
@@ -15,16 +16,32 @@ CODE_HOMREF, CODE_HET, CODE_MISSING, CODE_HOMALT = 0, 1, 2, 3
 
 
 def words_for(n_samples: int) -> int:
-    return max(1, (n_samples + 15) // 16)
+    """uint32 words per SNP of one population: a (lo plane, hi plane) pair per 32 samples."""
+    return 2 * max(1, (n_samples + 31) // 32)
 
 
 def _pack_block(codes: np.ndarray) -> np.ndarray:
+    """codes[S, ns] -> words[S, W]: word 2g = lo bits, word 2g+1 = hi bits of samples 32g .. 32g+31."""
     S, ns = codes.shape
     W = words_for(ns)
     padded = np.zeros((S, W * 16), dtype=np.uint32)
     padded[:, :ns] = codes
-    shifts = (2 * np.arange(16, dtype=np.uint32))[None, None, :]
-    return (padded.reshape(S, W, 16) << shifts).sum(axis=2, dtype=np.uint32)
+    g = padded.reshape(S, W // 2, 32)
+    shifts = np.arange(32, dtype=np.uint32)[None, None, :]
+    out = np.empty((S, W), dtype=np.uint32)
+    out[:, 0::2] = ((g & 1) << shifts).sum(axis=2, dtype=np.uint32)
+    out[:, 1::2] = ((g >> 1) << shifts).sum(axis=2, dtype=np.uint32)
+    return out
+
+
+def unpack_block(words: np.ndarray, ns: int) -> np.ndarray:
+    """words[S, W] of one population -> codes[S, ns] (inverse of _pack_block)."""
+    words = np.asarray(words, dtype=np.uint32)
+    S, W = words.shape
+    shifts = np.arange(32, dtype=np.uint32)[None, None, :]
+    lo = (words[:, 0::2, None] >> shifts) & np.uint32(1)
+    hi = (words[:, 1::2, None] >> shifts) & np.uint32(1)
+    return (lo | (hi << np.uint32(1))).reshape(S, -1)[:, :ns].astype(np.uint8)
 
 
 def to_b32(rows: np.ndarray) -> np.ndarray:
@@ -105,8 +122,7 @@ class PackedPanel:
         rows = from_b32(self.G, self.n, self.W1 + self.W2)
         out = np.zeros((self.n, 4), dtype=np.int64)
         for p, (w0, w1, ns) in enumerate(((0, self.W1, self.ns1), (self.W1, self.W1 + self.W2, self.ns2))):
-            blk = rows[:, w0:w1]
-            codes = np.stack([(blk >> np.uint32(2 * i)) & np.uint32(3) for i in range(16)], axis=-1).reshape(self.n, -1)[:, :ns]
+            codes = unpack_block(rows[:, w0:w1], ns)
             alt = (codes == CODE_HET).sum(1) + 2 * (codes == CODE_HOMALT).sum(1)
             out[:, 2 * p + 1] = alt
             out[:, 2 * p] = (codes == CODE_HET).sum(1) + 2 * (codes == CODE_HOMREF).sum(1)

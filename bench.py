@@ -38,7 +38,8 @@ WORKLOADS = {
 
 
 def words_for(n):
-    return max(1, (n + 15) // 16)
+    """uint32 words per SNP of one population: a (lo plane, hi plane) pair per 32 samples (tdsfs_pack.words_for)"""
+    return 2 * max(1, (n + 31) // 32)
 
 
 def chrom_sizes(S, C):

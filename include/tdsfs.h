@@ -104,11 +104,14 @@ int tdsfs_set_panel(tdsfs_t* ctx, int32_t n1, int32_t n2, int32_t fold);
 int tdsfs_load_counts(tdsfs_t* ctx, const uint16_t* cnt, int64_t S, const int32_t* pos, const int64_t* chrom_off,
                       int32_t C, const uint8_t* snp_flags);
 
-/* Genotype-level entry: 2-bit-per-call matrix.  Per SNP: RW = words1 + words2 uint32 words of 16 calls each
- * (call i of a word in bits 2i..2i+1), pop1 words then pop2 words, each population zero padded to a whole word.
+/* Genotype-level entry: 2-bit-per-call matrix, stored as bit planes.  Per SNP: RW = words1 + words2 uint32 words; a
+ * population is words/2 pairs (lo word, hi word) of 32 samples each: bit b of the lo / hi word of pair g is the low /
+ * high bit of the code of sample 32g + b.  pop1 pairs then pop2 pairs, each population zero padded to a whole pair
+ * (words1, words2 even: words = 2 * ceil(samples / 32)).
  * Memory layout "B32" (block transposed): SNPs in blocks of 32; word w of SNP s at uint32 index
  * ((s / 32) * RW + w) * 32 + s % 32; the buffer holds ceil(S / 32) whole blocks (rows beyond S zero).
- * Codes: 0 = 0/0, 1 = 0/1, 3 = 1/1, 2 = missing.  ns1/ns2 = number of sample columns in each block.
+ * Codes: 0 = 0/0, 1 = 0/1, 3 = 1/1, 2 = missing, so #missing = popcount(hi & ~lo), alt = popcount(all words) - #missing,
+ * ref = 2 * (samples - #missing) - alt.  ns1/ns2 = number of sample columns in each block.
  * Replaces the per-sample counting loop of make_data_dict_vcf (:118-130).  Host G is uploaded in chunks
  * asynchronously; the upload overlaps the count kernel of tdsfs_background. */
 int tdsfs_load_genotypes(tdsfs_t* ctx, const void* G, int64_t S, int32_t words1, int32_t words2, int32_t ns1,

@@ -67,7 +67,9 @@ static void decode_chunk(void* a, int64_t ci) {
       const int ns = pop ? ns2 : ns1;
       int ref = 0, alt = 0;
       for (int i = 0; i < ns; ++i) { /* one sample at a time, as the reference does */
-        const unsigned code = (blk[(i >> 4) * 32] >> (2 * (i & 15))) & 3u;
+        /* samples 32g..32g+31: word 2g holds the lo bits of their codes, word 2g+1 the hi bits */
+        const unsigned lo = (blk[(2 * (i >> 5)) * 32] >> (i & 31)) & 1u, hi = (blk[(2 * (i >> 5) + 1) * 32] >> (i & 31)) & 1u;
+        const unsigned code = lo | (hi << 1);
         if (code == 0) ref += 2;
         else if (code == 1) { ref += 1; alt += 1; }
         else if (code == 3) alt += 2; /* code 2 = missing: counts nothing */

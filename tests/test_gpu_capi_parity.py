@@ -138,7 +138,7 @@ def random_panel(rng, S, ns1, ns2, C, L, miss=0.03):
     (18, 14, 20000, 3, 400000, 20000),      # ECB geometry: 2 + 1 words (unaligned rows)
     (5, 5, 30000, 40, 60000, 5000),         # sims geometry: 1 + 1 words, many chromosomes
     (64, 64, 30000, 4, 300000, 10000),      # 4 + 4 words: aligned path
-    (200, 200, 40000, 5, 400000, 20000),    # config-4 geometry: 13 + 13 words, hash scorer
+    (200, 200, 40000, 5, 400000, 20000),    # config-4 geometry: 14 + 14 words, hash scorer
     (500, 500, 12000, 2, 200000, 20000),    # config-5 geometry: 32 + 32 words, aligned + rotation
     (100, 37, 9000, 2, 100000, 7000),       # asymmetric
 ])
@@ -284,17 +284,16 @@ def test_synthetic_generator_statistics(T, h):
     """The on-device synthetic panel (bench input): codes legal, missing rate ~2 %, padding zero, deterministic."""
     import torch
     S, ns1, ns2 = 4096, 200, 200
-    w1 = w2 = 13
+    w1 = w2 = 14
     g = torch.zeros(((S + 31) // 32 * (w1 + w2) * 32,), dtype=torch.int32, device="cuda")
     h.synth_genotypes(g.data_ptr(), S, 1000, w1, w2, ns1, ns2, 20241004)
     g2 = torch.zeros_like(g)
     h.synth_genotypes(g2.data_ptr(), S, 1000, w1, w2, ns1, ns2, 20241004)
     assert torch.equal(g, g2)
-    from tdsfs_pack import from_b32
+    from tdsfs_pack import from_b32, unpack_block
     Gb = g.cpu().numpy().view(np.uint32)
     G = from_b32(Gb, S, w1 + w2)
-    codes = np.stack([(G >> (2 * i)) & 3 for i in range(16)], axis=-1).reshape(S, -1)
-    pop1 = codes[:, :w1 * 16]
+    pop1 = unpack_block(G[:, :w1], w1 * 16)
     assert (pop1[:, ns1:] == 0).all()
     miss = (pop1[:, :ns1] == 2).mean()
     assert 0.015 < miss < 0.025
