@@ -505,6 +505,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   }
 
   const int hist_bytes = (p.cr * p.cc + p.h1a + p.h1b) * 4;
+  if (const char* e = getenv("TDSFS_K1_DEBUG")) p.debug = atoi(e);  // profiling only: results are wrong
   if (c->dG) {
     const int RW = c->W1 + c->W2;
     const int blk_bytes = RW * BLK * 4;

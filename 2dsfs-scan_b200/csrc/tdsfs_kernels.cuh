@@ -55,6 +55,7 @@ struct KeyParams {
   int nstage, stage_bytes;  // K1 ring: stages of `tile_blocks` 32-SNP blocks; nstage is a multiple of cwarps
   int tile_blocks;
   int cwarps;               // active consumer warps (<= K1_CWARPS)
+  int debug;                // profiling only (TDSFS_K1_DEBUG): bit 0 = no record store, bit 1 = no histogram updates
   int interleave;           // 1: tile i of the launch goes to CTA i % grid (all SMs stream one moving window of the matrix);
                             // 0: contiguous tile range per CTA (keeps a CTA inside one background group)
 };
@@ -310,6 +311,7 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
       key = (uint32_t)(k1 * p.C2 + k2);  // (0,0) -> 0 : skipped SNP (:212)
       alts = (uint32_t)folded_interior(alt1, p.n1) | ((uint32_t)folded_interior(alt2, p.n2) << 16);
       int g = group_of_row(p, s, cc);
+      if (p.debug & 2) g = -1;
       if (g >= 0) {
         uint32_t* gh = p.hist + (long long)g * p.gstride;
         if (key) {
@@ -326,6 +328,10 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
         }
       }
     }
+  }
+  if (p.debug & 1) {
+    if (key == 0xFFFFFFFFu) __stcs(p.rec + s, make_uint2(key, alts));
+    return;
   }
   __stcs(p.rec + s, make_uint2(key, alts));  // streaming store: read once by the scorer, from L2 or HBM
 }
