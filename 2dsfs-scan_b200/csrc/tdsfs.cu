@@ -122,6 +122,8 @@ struct tdsfs_ctx {
   uint8_t* r_flags = nullptr;
   uint32_t* d_scratch = nullptr;
   int large_ctas = 0;
+  unsigned long long* d_work = nullptr;  // window hand-out counter of the scorer (monotonic, never reset)
+  unsigned long long work_base = 0;
   bool results_ready = false;
   // instrumentation
   cudaEvent_t ev[NEV] = {};
@@ -231,6 +233,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   if (c->pool_flags) cudaFree(c->pool_flags);
   peer_unmap(c);
   dev_free(c->d_peer_flags);
+  dev_free(c->d_work);
   dev_free(c->d_rec); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
   dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
   dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
@@ -960,6 +963,14 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       occ = std::max(1, occ);
       const long long want = (ncand + (SCORE_WARPS / G) - 1) / (SCORE_WARPS / G);
       const int grid = (int)std::min<long long>(want, (long long)c->sm_count * occ);
+      if (!c->d_work) {
+        CKR(dev_alloc(&c->d_work, 1));
+        CK(cudaMemsetAsync(c->d_work, 0, 8, st));
+        c->work_base = 0;
+      }
+      s.work = c->d_work;
+      s.work_base = c->work_base;
+      c->work_base += (unsigned long long)ncand + (unsigned long long)grid * (SCORE_WARPS / G);
       sk<<<grid, SCORE_WARPS * 32, smem, st>>>(s);
       c->launches++;
     }

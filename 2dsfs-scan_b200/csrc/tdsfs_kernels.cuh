@@ -885,6 +885,10 @@ struct ScoreParams {
   const int32_t* score_group;  // per chromosome (NULL = group 0)
   long long ncand;
   int n1, n2, bins2d, snp_mode;
+  // dynamic window assignment: a group takes window atomicAdd(work, 1) - work_base until that is >= ncand; every group
+  // fails exactly once per launch, so the host advances work_base by ncand + groups and the counter never needs a reset
+  unsigned long long* work;
+  unsigned long long work_base;
   const double* lb2;
   const double* lb1a;
   const double* lb1b;
@@ -960,7 +964,7 @@ constexpr int SCORE_WARPS = 8;
 constexpr int KEY_SHIFT = 10;  // multiplicity field (< 1024, WCAP = 768)
 __host__ __device__ inline int score_group_smem_words(int n1, int n2) {
   // table | 1D bins (padded to an even word count) | reduction scratch (SCORE_WARPS x 10 words)
-  return HASH_SLOTS + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + SCORE_WARPS * 10;
+  return HASH_SLOTS + (((n1 + 2) / 2 + (n2 + 2) / 2 + 1) & ~1) + SCORE_WARPS * 10 + 2;
 }
 // limits of the shared-memory scorer; panels beyond them are scored by the CTA kernel only
 __host__ __device__ inline bool score_small_ok(int n1, int n2, int bins2d) {
@@ -1003,8 +1007,23 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   const bool has_flags = EXTRA && p.flags != nullptr;
   const bool snp_mode = EXTRA && p.snp_mode;
 
-  const long long ngroups = (long long)gridDim.x * GROUPS;
-  for (long long id = (long long)blockIdx.x * GROUPS + grp; id < p.ncand; id += ngroups) {
+  // windows are handed out dynamically (an atomic counter): with a few windows per warp a static round-robin leaves
+  // most warps idle while the ones that drew one window more finish
+  auto grab = [&]() -> long long {
+    long long v = 0;
+    if (G == 1) {
+      if (lane == 0) v = (long long)(atomicAdd(p.work, 1ull) - p.work_base);
+      v = __shfl_sync(0xffffffffu, v, 0);
+    } else {
+      volatile long long* slot = reinterpret_cast<volatile long long*>(red + SCORE_WARPS * 10);
+      if (tg == 0) *slot = (long long)(atomicAdd(p.work, 1ull) - p.work_base);
+      gsync();
+      v = *slot;
+      gsync();
+    }
+    return v;
+  };
+  for (long long id = grab(); id < p.ncand; id = grab()) {
     const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
     const int cnt = hi - lo;
     if (cnt == 0) {
