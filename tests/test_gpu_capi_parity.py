@@ -195,7 +195,7 @@ def test_counts_entry_equals_genotype_entry_and_window_spectra(T, h):
     b = h.run_bp(T.BG_GENOME, 4000)
     for k in a:
         if a[k].dtype == np.float64:  # fp64 sums run in atomic-arrival order: equal to rounding, not bitwise
-            assert np.allclose(a[k], b[k], rtol=1e-12, atol=1e-12, equal_nan=True), k
+            assert np.allclose(a[k], b[k], rtol=1e-11, atol=1e-11, equal_nan=True), k
         else:
             assert np.array_equal(a[k], b[k]), k
     # spectra of single windows (calculate_2d_sfs / calculate_1d_sfs on window_data)
@@ -373,7 +373,7 @@ def test_peer_exchange_single_rank(T, h):
         res = h.scan(6000)
     for k in plain:
         if plain[k].dtype == np.float64:
-            assert np.allclose(res[k], plain[k], rtol=1e-12, atol=1e-12, equal_nan=True), k
+            assert np.allclose(res[k], plain[k], rtol=1e-11, atol=1e-11, equal_nan=True), k
         else:
             assert np.array_equal(res[k], plain[k]), k
     h.background(T.BG_PER_CHROM)                  # several groups: the exchange refuses

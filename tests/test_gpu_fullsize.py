@@ -85,5 +85,5 @@ def test_config4_full_size_properties():
             assert not none
             got = res[name][wid]
             assert abs(got - exp) <= 1e-9 * max(abs(exp), 1.0), (wid, name, got, exp)
-    assert np.allclose(h.fetch_results(len(res["start"]))["T2D"][live], T2_genome[live], rtol=1e-12, atol=1e-12)
+    assert np.allclose(h.fetch_results(len(res["start"]))["T2D"][live], T2_genome[live], rtol=1e-11, atol=1e-11)
     h.close()
