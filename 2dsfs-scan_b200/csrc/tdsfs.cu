@@ -85,7 +85,7 @@ struct tdsfs_ctx {
   int32_t* d_bg_group = nullptr;
   int32_t* d_score_group = nullptr;
   bool per_chrom_scoring = false;
-  double *d_lb2 = nullptr, *d_lb1a = nullptr, *d_lb1b = nullptr, *d_B = nullptr, *d_lnI = nullptr, *d_dxI = nullptr;
+  double *d_lb2 = nullptr, *d_lb1a = nullptr, *d_lb1b = nullptr, *d_B = nullptr, *d_lnI = nullptr;
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
   bool float_bg = false, tables_ready = false, fin_timed = false;
@@ -188,10 +188,8 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   CKR(dev_alloc(&c->d_nlarge, 1));
   CKR(dev_alloc(&c->d_lnI, LN_TABLE));
   CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-  CKR(dev_alloc(&c->d_dxI, LN_TABLE));
   k_ln_int_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_lnI, LN_TABLE);
-  k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
-  c->launches += 2;
+  c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
@@ -237,7 +235,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   dev_free(c->d_peer_flags);
   dev_free(c->d_work);
   dev_free(c->d_rec); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
-  dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI); dev_free(c->d_dxI);
+  dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
   dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
   dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend); dev_free(c->d_nlarge);
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
@@ -941,7 +939,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     s.rec = c->d_rec; s.flags = c->dFlags; s.wlo = c->d_wlo; s.whi = c->d_whi; s.wchrom = c->d_wchrom;
     s.score_group = c->per_chrom_scoring ? c->d_score_group : nullptr;
     s.ncand = ncand; s.n1 = c->n1; s.n2 = c->n2; s.bins2d = c->bins2d; s.snp_mode = snp_mode;
-    s.lb2 = c->d_lb2; s.lb1a = c->d_lb1a; s.lb1b = c->d_lb1b; s.B = c->d_B; s.lnI = c->d_lnI; s.dxI = c->d_dxI;
+    s.lb2 = c->d_lb2; s.lb1a = c->d_lb1a; s.lb1b = c->d_lb1b; s.B = c->d_B; s.lnI = c->d_lnI;
     s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
     // small windows: one warp each
@@ -957,20 +955,8 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       while (G < SCORE_WARPS && (SCORE_WARPS / G) * gwords * 4 > 200 * 1024) G *= 2;  // fewer, wider groups for big panels
       const int smem = (SCORE_WARPS / G) * gwords * 4;
       const bool extra = snp_mode || c->dFlags != nullptr;
-      // Scorer variant.  Default: incremental sums (k3_score_incr), with the 1D spectra incremental too when their walk
-      // would be long (large panels); TDSFS_K3_MODE = walk | incr1d | incr2d forces the table-walk scorer
-      // (k3_score_small) / 1D incremental / 1D walked.  The incremental kernels index the ln b tables with 32 bits.
-      const char* k3m = getenv("TDSFS_K3_MODE");
-      const long long table_elems = (long long)std::max(1, c->table_groups) * c->bins2d;
-      const bool incr = !(k3m && strcmp(k3m, "walk") == 0) && table_elems < (1LL << 32);
-      bool d1 = (c->n1 + 2) / 2 + (c->n2 + 2) / 2 >= 384;
-      if (k3m && strcmp(k3m, "incr1d") == 0) d1 = true;
-      if (k3m && strcmp(k3m, "incr2d") == 0) d1 = false;
-      void (*sk)(ScoreParams);
-#define TDSFS_PICK(K, ...) (G >= 8 ? K<8, __VA_ARGS__> : (G == 4 ? K<4, __VA_ARGS__> : (G == 2 ? K<2, __VA_ARGS__> : K<1, __VA_ARGS__>)))
-      if (incr && d1) sk = extra ? TDSFS_PICK(k3_score_incr, true, true) : TDSFS_PICK(k3_score_incr, false, true);
-      else if (incr) sk = extra ? TDSFS_PICK(k3_score_incr, true, false) : TDSFS_PICK(k3_score_incr, false, false);
-      else sk = extra ? TDSFS_PICK(k3_score_small, true) : TDSFS_PICK(k3_score_small, false);
+#define TDSFS_PICK(K, E) (G >= 8 ? K<8, E> : (G == 4 ? K<4, E> : (G == 2 ? K<2, E> : K<1, E>)))
+      void (*sk)(ScoreParams) = extra ? TDSFS_PICK(k3_score_small, true) : TDSFS_PICK(k3_score_small, false);
 #undef TDSFS_PICK
       CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 1;

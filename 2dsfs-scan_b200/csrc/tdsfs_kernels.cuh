@@ -804,12 +804,6 @@ __global__ void k_ln_int_table(double* t, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = i ? log((double)i) : 0.0;
 }
-// dx[m] = (m+1) ln(m+1) - m ln m, the change of x ln x when a bin goes from m to m+1 SNPs; written as
-// ln(m+1) + m log1p(1/m) so that no large terms cancel
-__global__ void k_dx_table(double* t, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) t[i] = i ? log((double)i + 1.0) + (double)i * log1p(1.0 / (double)i) : 0.0;
-}
 
 // ------------------------------------------------------------------------------------------------ K2 boundaries
 struct WinParams {
@@ -900,7 +894,6 @@ struct ScoreParams {
   const double* lb1b;
   const double* B;       // [NG][6]: interior totals B (2D, 1D pop1, 1D pop2), then ln B
   const double* lnI;     // ln(m), m < LN_TABLE
-  const double* dxI;     // (m+1) ln(m+1) - m ln m, m < LN_TABLE (k3_score_incr)
   // outputs
   int32_t* r_count;
   int32_t* r_n2;
@@ -994,8 +987,7 @@ __device__ __forceinline__ void bump_half_if(uint32_t* h, uint32_t f) {
 template <int G, bool EXTRA>
 __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_constant__ ScoreParams p) {
   extern __shared__ __align__(16) uint32_t sm32[];
-  constexpr int GT = G * 32;                 // threads per group
-  constexpr int GROUPS = SCORE_WARPS / G;    // groups per CTA
+  constexpr int GT = G * 32;                 // threads per group (SCORE_WARPS / G groups per CTA)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = warp / G, wg = warp % G, tg = wg * 32 + lane;
   const int gwords = score_group_smem_words(p.n1, p.n2);
@@ -1170,304 +1162,6 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
       bool none = false;
       double Tq = 0.0;
       if (lane < 3) Tq = clr_value(p, Nq, aq, p.B + g * 6, lane, none);
-      const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
-      if (lane == 0) {
-        uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
-        if (p.snp_mode && nall == 0) f |= TDSFS_F_SKIPPED;
-        p.r_count[id] = count;
-        p.r_flags[id] = f;
-        p.r_T2[id] = Tq;
-        p.r_n2[id] = Nq;
-      } else if (lane == 1) {
-        p.r_T1a[id] = Tq;
-        p.r_n1a[id] = Nq;
-      } else if (lane == 2) {
-        p.r_T1b[id] = Tq;
-        p.r_n1b[id] = Nq;
-      }
-    }
-    gsync();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ K3+K4, incremental form
-// Same windows, tables and record format as k3_score_small, but the 2D likelihood sum (and, with D1, both 1D sums) is
-// accumulated WHILE the spectrum is built: inserting a SNP into a bin that already holds c SNPs changes that bin's term
-// x (ln x - ln b) by
-//     (c+1) ln(c+1) - c ln c - ln b  =  dx[c] - ln b          (dx[0] = 0, dx from a 4096-entry table)
-// and the atomic that bumps the bin returns c, so   sum_bins x (ln x - ln b) = sum_SNPs (dx[c_s] - ln b[bin_s])
-// whatever the arrival order.  The ln b gather depends on the record only (issued before the probe loop, in flight with
-// it) and the table walk of k3_score_small shrinks to clearing the table with 8-byte stores.
-//   D1 = true : the two 1D spectra are scored the same way (shared-memory atomics that return the old count); the 1D
-//               walk disappears as well.  Pays when the 1D walk is long (large panels: (n1 + n2) / 2 words per window).
-//   D1 = false: 1D bins are bumped with predicated reductions and walked afterwards like k3_score_small (small panels).
-// The per-bin form is still needed for the two spectra where the reference returns exactly 0.0 (its truthiness drives
-// the stale-carry quirk): a window that is its own background (then N == B) and a window whose only
-// populated bin is the background's only bin (then the largest "old count" seen is N - 1).  Those windows are re-scored
-// by walking the tables with the explicit roundings of k3_score_small (exact_walk_*).
-template <int G>
-__device__ __forceinline__ void exact_walk_table(const ScoreParams& p, uint32_t* tab, int tg, const double* lb2, double& a2) {
-  constexpr int GT = G * 32;
-  for (int j = tg; j < HASH_SLOTS; j += GT) {
-    const uint32_t e = tab[j];
-    if (e != EMPTY_KEY) {
-      tab[j] = EMPTY_KEY;
-      const uint32_t x = e & ((1u << KEY_SHIFT) - 1);
-      const double lnx = x > 1 ? __ldg(p.lnI + x) : 0.0;
-      a2 = fma(u32_to_double(x), lnx - __ldg(lb2 + (e >> KEY_SHIFT)), a2);
-    }
-  }
-}
-template <int G>
-__device__ __forceinline__ void exact_walk_1d(const ScoreParams& p, uint32_t* h1, int nw, int tg, const double* lb, double& acc) {
-  constexpr int GT = G * 32;
-  for (int w = tg; w < nw; w += GT) {
-    const uint32_t v = h1[w];
-    if (v) {
-      h1[w] = 0;
-      const uint32_t x0 = v & 0xFFFF, x1 = v >> 16;
-      if (x0) acc = fma(u32_to_double(x0), (x0 > 1 ? __ldg(p.lnI + x0) : 0.0) - __ldg(lb + 2 * w), acc);
-      if (x1) acc = fma(u32_to_double(x1), (x1 > 1 ? __ldg(p.lnI + x1) : 0.0) - __ldg(lb + 2 * w + 1), acc);
-    }
-  }
-}
-// 1D walk of k3_score_small (pass 3): four words = eight bins per thread in flight, bins cleared on the way
-template <int G>
-__device__ __forceinline__ void walk_1d_batched(const ScoreParams& p, uint32_t* h1, int nw, int tg, const double* lb, double& acc,
-                                                uint32_t& N) {
-  constexpr int GT = G * 32;
-  constexpr int U = 4;
-#pragma unroll 1
-  for (int w0 = tg; w0 < nw; w0 += U * GT) {
-    uint32_t v[U];
-    double lbv[2 * U], lnx[2 * U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int w = w0 + u * GT;
-      v[u] = w < nw ? h1[w] : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int w = w0 + u * GT;
-      const uint32_t x0 = v[u] & 0xFFFF, x1 = v[u] >> 16;
-      lbv[2 * u] = x0 ? __ldg(lb + 2 * w) : 0.0;
-      lbv[2 * u + 1] = x1 ? __ldg(lb + 2 * w + 1) : 0.0;
-      lnx[2 * u] = x0 > 1 ? __ldg(p.lnI + x0) : 0.0;
-      lnx[2 * u + 1] = x1 > 1 ? __ldg(p.lnI + x1) : 0.0;
-      if (v[u]) h1[w] = 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t x0 = v[u] & 0xFFFF, x1 = v[u] >> 16;
-      if (x0) acc = fma(u32_to_double(x0), lnx[2 * u] - lbv[2 * u], acc);
-      if (x1) acc = fma(u32_to_double(x1), lnx[2 * u + 1] - lbv[2 * u + 1], acc);
-      N += x0 + x1;
-    }
-  }
-}
-
-template <int G, bool EXTRA, bool D1>
-__global__ void __launch_bounds__(SCORE_WARPS * 32, 4) k3_score_incr(const __grid_constant__ ScoreParams p) {
-  extern __shared__ __align__(16) uint32_t sm32[];
-  constexpr int GT = G * 32;                 // threads per group
-  constexpr uint32_t F10 = (1u << KEY_SHIFT) - 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = warp / G, wg = warp % G, tg = wg * 32 + lane;
-  const int gwords = score_group_smem_words(p.n1, p.n2);  // even: every group starts 8-byte aligned
-  uint32_t* tab = sm32 + (size_t)grp * gwords;
-  uint32_t* h1a = tab + HASH_SLOTS;            // packed 16-bit bins: bin f in word f >> 1, half f & 1
-  const int nw1 = (p.n1 + 2) / 2, nw2 = (p.n2 + 2) / 2;
-  uint32_t* h1b = h1a + nw1;
-  const int nw12 = (nw1 + nw2 + 1) & ~1;       // words of both 1D histograms, padded to an even count
-  uint32_t* red = h1a + nw12;                  // [G][10] (8-byte aligned): per warp {a2, a1a, a1b (doubles), N-pack, count, nall, max-pack}
-  auto gsync = [&]() {
-    if (G == 1) __syncwarp(); else named_bar_sync(1 + grp, GT);
-  };
-  auto clear_table = [&]() {  // 8-byte stores
-    uint2* t2 = reinterpret_cast<uint2*>(tab);
-#pragma unroll
-    for (int i = 0; i < HASH_SLOTS / 2 / GT; ++i) t2[tg + i * GT] = make_uint2(EMPTY_KEY, EMPTY_KEY);
-  };
-  auto clear_1d = [&]() {
-    uint2* h2 = reinterpret_cast<uint2*>(h1a);
-    for (int i = tg; i < nw12 / 2; i += GT) h2[i] = make_uint2(0u, 0u);
-  };
-  clear_table();
-  clear_1d();
-  gsync();
-  const uint32_t last = (uint32_t)p.bins2d - 1;
-  const bool has_flags = EXTRA && p.flags != nullptr;
-  const bool snp_mode = EXTRA && p.snp_mode;
-
-  auto grab = [&]() -> long long {  // dynamic window hand-out, see k3_score_small
-    long long v = 0;
-    if (G == 1) {
-      if (lane == 0) v = (long long)(atomicAdd(p.work, 1ull) - p.work_base);
-      v = __shfl_sync(0xffffffffu, v, 0);
-    } else {
-      volatile long long* slot = reinterpret_cast<volatile long long*>(red + SCORE_WARPS * 10);
-      if (tg == 0) *slot = (long long)(atomicAdd(p.work, 1ull) - p.work_base);
-      gsync();
-      v = *slot;
-      gsync();
-    }
-    return v;
-  };
-  for (long long id = grab(); id < p.ncand; id = grab()) {
-    const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
-    const int cnt = hi - lo;
-    if (cnt == 0) {
-      if (tg == 0) { p.r_count[id] = 0; p.r_flags[id] = TDSFS_F_EMPTY; }
-      continue;
-    }
-    if (cnt > WCAP) continue;  // scored by k3_score_large
-    const int g = p.score_group ? __ldg(p.score_group + __ldg(p.wchrom + id)) : 0;
-    // 32-bit element offsets of the group's ln b tables (the host checks groups x bins < 2^32): one add + one scaled
-    // add per gather instead of 64-bit pointer arithmetic
-    const uint32_t o2 = (uint32_t)g * (uint32_t)p.bins2d;
-    const uint32_t o1a = (uint32_t)g * (uint32_t)(p.n1 + 1), o1b = (uint32_t)g * (uint32_t)(p.n2 + 1);
-
-    // ---- the one pass over the window's records: Q records and their ln b gathers per thread in flight
-    constexpr int Q = G == 1 ? 8 : 4;
-    int count = 0, nall = 0;
-    double a2 = 0.0, a1a = 0.0, a1b = 0.0;
-    // nn: SNPs entering each likelihood, packed 2D | 1D pop1 << 10 | 1D pop2 << 20 (window totals <= WCAP < 1024)
-    // m2 / m1a / m1b: largest old count returned by a bin update (N - 1 iff every SNP fell into one bin)
-    uint32_t nn = 0, m2 = 0, m1a = 0, m1b = 0;
-    for (int base = 0; base < cnt; base += Q * GT) {
-      uint2 r[Q];
-      double l2[Q];
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int i = base + q * GT + tg;
-        r[q] = i < cnt ? __ldcs(p.rec + lo + i) : make_uint2(0u, 0u);  // streamed once: keep the ln b table in L2
-        if (has_flags && i < cnt) count += (__ldg(p.flags + lo + i) >> 1) & 1;
-      }
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint32_t k = r[q].x;
-        l2[q] = (k != 0 && k != last) ? __ldg(p.lb2 + (o2 + k)) : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint32_t k = r[q].x;
-        if (snp_mode) nall += k != 0;
-        if (k != 0 && k != last) {
-          uint32_t h = (k * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
-          uint32_t c;                            // SNPs already in the bin
-          while (true) {  // read first: a shared-memory CAS costs about twice a load or an add
-            uint32_t e = tab[h];
-            if (e == EMPTY_KEY) {
-              e = atomicCAS(tab + h, EMPTY_KEY, (k << KEY_SHIFT) | 1u);
-              if (e == EMPTY_KEY) { c = 0; break; }
-            }
-            if ((e >> KEY_SHIFT) == k) { c = atomicAdd(tab + h, 1u) & F10; break; }
-            h = (h + 1) & (HASH_SLOTS - 1);
-          }
-          a2 += __ldg(p.dxI + c) - l2[q];
-          nn += 1u;
-          m2 = max(m2, c);
-        }
-        const uint32_t fa = r[q].y & 0xFFFF, fb = r[q].y >> 16;
-        if (D1) {
-          if (fa) {
-            const uint32_t sh = (fa & 1u) << 4;
-            const uint32_t c = (atomicAdd(h1a + (fa >> 1), 1u << sh) >> sh) & 0xFFFFu;
-            a1a += __ldg(p.dxI + c) - __ldg(p.lb1a + (o1a + fa));
-            nn += 1u << 10;
-            m1a = max(m1a, c);
-          }
-          if (fb) {
-            const uint32_t sh = (fb & 1u) << 4;
-            const uint32_t c = (atomicAdd(h1b + (fb >> 1), 1u << sh) >> sh) & 0xFFFFu;
-            a1b += __ldg(p.dxI + c) - __ldg(p.lb1b + (o1b + fb));
-            nn += 1u << 20;
-            m1b = max(m1b, c);
-          }
-        } else {
-          bump_half_if(h1a, fa);
-          bump_half_if(h1b, fb);
-        }
-      }
-    }
-    // ---- reduce: warp level, then across the group's warps through shared memory (every thread ends with the totals)
-    nn = __reduce_add_sync(0xffffffffu, nn);
-    uint32_t mm = __reduce_max_sync(0xffffffffu, m2);
-    if (D1) mm |= (__reduce_max_sync(0xffffffffu, m1a) << 10) | (__reduce_max_sync(0xffffffffu, m1b) << 20);
-    if (has_flags) count = __reduce_add_sync(0xffffffffu, count);
-    if (snp_mode) nall = __reduce_add_sync(0xffffffffu, nall);
-    a2 = warp_sum(a2);
-    if (D1) { a1a = warp_sum(a1a); a1b = warp_sum(a1b); }
-    auto group_sum = [&]() {  // G > 1: totals over the group's warps (counters: sums; old-count maxima: per-field max)
-      if (lane == 0) {
-        double* rd = reinterpret_cast<double*>(red + wg * 10);
-        rd[0] = a2; rd[1] = a1a; rd[2] = a1b;
-        red[wg * 10 + 6] = nn; red[wg * 10 + 7] = (uint32_t)count; red[wg * 10 + 8] = (uint32_t)nall; red[wg * 10 + 9] = mm;
-      }
-      gsync();
-      a2 = a1a = a1b = 0.0; nn = 0; count = 0; nall = 0;
-      uint32_t x2 = 0, x1a = 0, x1b = 0;
-#pragma unroll
-      for (int w = 0; w < G; ++w) {
-        const double* rd = reinterpret_cast<const double*>(red + w * 10);
-        a2 += rd[0]; a1a += rd[1]; a1b += rd[2];
-        nn += red[w * 10 + 6]; count += (int)red[w * 10 + 7]; nall += (int)red[w * 10 + 8];
-        const uint32_t m = red[w * 10 + 9];
-        x2 = max(x2, m & F10); x1a = max(x1a, (m >> 10) & F10); x1b = max(x1b, m >> 20);
-      }
-      mm = x2 | (x1a << 10) | (x1b << 20);
-    };
-    // the synchronisation also orders every insert of the window before the tables are cleared / walked
-    if (G == 1) gsync(); else group_sum();
-    const double* Bg = p.B + g * 6;
-    int N2 = (int)(nn & F10), N1a = (int)((nn >> 10) & F10), N1b = (int)(nn >> 20);
-    bool exact = N2 > 0 && ((int)(mm & F10) + 1 == N2 || (double)N2 == __ldg(Bg));
-    if (D1)
-      exact = exact || (N1a > 0 && ((int)((mm >> 10) & F10) + 1 == N1a || (double)N1a == __ldg(Bg + 1))) ||
-              (N1b > 0 && ((int)(mm >> 20) + 1 == N1b || (double)N1b == __ldg(Bg + 2)));
-    const double* lb1a = p.lb1a + o1a;
-    const double* lb1b = p.lb1b + o1b;
-    if (!exact) {
-      clear_table();
-      if (D1) clear_1d();
-    } else {  // rare: per-bin form with the explicit roundings (clears the tables on the way)
-      a2 = 0.0;
-      exact_walk_table<G>(p, tab, tg, p.lb2 + o2, a2);
-      if (D1) {
-        a1a = a1b = 0.0;
-        exact_walk_1d<G>(p, h1a, nw1, tg, lb1a, a1a);
-        exact_walk_1d<G>(p, h1b, nw2, tg, lb1b, a1b);
-      }
-    }
-    if (!D1) {  // 1D spectra: per-bin walk (also yields N1a / N1b)
-      uint32_t w1a = 0, w1b = 0;
-      a1a = a1b = 0.0;
-      walk_1d_batched<G>(p, h1a, nw1, tg, lb1a, a1a, w1a);
-      walk_1d_batched<G>(p, h1b, nw2, tg, lb1b, a1b, w1b);
-      nn = w1a | (w1b << 10);  // per-thread partials again
-    }
-    if (!D1 || exact) {  // uniform over the group: a second reduction of what the walks produced
-      const int N2k = N2, N1ak = N1a, N1bk = N1b, countk = count, nallk = nall;
-      if (exact) a2 = warp_sum(a2);
-      a1a = warp_sum(a1a); a1b = warp_sum(a1b);
-      if (!D1) nn = __reduce_add_sync(0xffffffffu, nn);
-      if (G > 1) {
-        const double a2k = a2;
-        gsync();  // every thread has read the first reduction
-        group_sum();
-        if (!exact) a2 = a2k;  // already the group total
-      }
-      N2 = N2k; count = countk; nall = nallk;
-      if (D1) { N1a = N1ak; N1b = N1bk; }
-      else { N1a = (int)(nn & F10); N1b = (int)((nn >> 10) & F10); }
-    }
-    if (wg == 0) {  // lanes 0..2 finish one statistic each (ln N from the multiplicity table, ln B precomputed)
-      if (!has_flags) count = cnt;
-      const int Nq = lane == 0 ? N2 : (lane == 1 ? N1a : N1b);
-      const double aq = lane == 0 ? a2 : (lane == 1 ? a1a : a1b);
-      bool none = false;
-      double Tq = 0.0;
-      if (lane < 3) Tq = clr_value(p, Nq, aq, Bg, lane, none);
       const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
       if (lane == 0) {
         uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4

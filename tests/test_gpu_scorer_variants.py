@@ -1,9 +1,8 @@
-"""Every variant of the window scorer against the CPU oracle on the same inputs: the table-walk kernel (k3_score_small),
-the incremental kernel with walked 1D spectra (k3_score_incr<.., D1=false>) and with incremental 1D spectra (D1=true),
-each with 1, 2 and 4 warps per window.  The library picks a variant from the panel size and the scan size; the tuning
-knobs TDSFS_K3_MODE / TDSFS_SCORE_G (read at every scan) force one so that all of them are parity-tested on small inputs.
-Includes the spectra for which the reference returns exactly 0.0 (its truthiness drives the stale-carry
-quirk): a window that is its own background, and a window whose only bin is the background's only bin."""
+"""Every instantiation of the shared-memory window scorer (k3_score_small with 1, 2 and 4 warps per window) against the
+CPU oracle on the same inputs.  The library picks the group width from the scan size; the tuning knob TDSFS_SCORE_G
+(read at every scan) forces one so that all of them are parity-tested on small inputs.  Includes the spectra for which
+the reference returns exactly 0.0 (its truthiness drives the stale-carry quirk): a window that is its
+own background, and a window whose only bin is the background's only bin."""
 import os
 
 import numpy as np
@@ -13,8 +12,6 @@ import sfs_oracle as O
 from test_gpu_capi_parity import compare_scan, random_panel
 
 pytestmark = pytest.mark.gpu
-
-MODES = ["walk", "incr2d", "incr1d"]
 
 
 @pytest.fixture(scope="module")
@@ -32,10 +29,9 @@ def h(T):
 
 @pytest.fixture()
 def knobs():
-    saved = {k: os.environ.get(k) for k in ("TDSFS_K3_MODE", "TDSFS_SCORE_G")}
+    saved = {k: os.environ.get(k) for k in ("TDSFS_SCORE_G",)}
 
-    def set_(mode, G):
-        os.environ["TDSFS_K3_MODE"] = mode
+    def set_(G):
         os.environ["TDSFS_SCORE_G"] = str(G)
     yield set_
     for k, v in saved.items():
@@ -46,16 +42,15 @@ def knobs():
 
 
 @pytest.mark.parametrize("G", [1, 2, 4])
-@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("n1,n2,S,C,L,W,N", [
     (18, 14, 12000, 3, 300000, 20000, 250),    # ECB geometry, ~800 SNPs per window: small and large windows mixed
     (200, 37, 9000, 2, 100000, 6000, 300),     # asymmetric panel, ~270 SNPs per window
 ])
-def test_variant_vs_oracle(T, h, knobs, mode, G, n1, n2, S, C, L, W, N):
+def test_variant_vs_oracle(T, h, knobs, G, n1, n2, S, C, L, W, N):
     rng = np.random.default_rng(n1 * 7 + n2 + S)
     Gm, w1, w2, pos, off = random_panel(rng, S, n1, n2, C, L)
     cnt = O.unpack_counts(Gm, w1, w2, n1, n2, S)
-    knobs(mode, G)
+    knobs(G)
     h.set_panel(n1, n2, True)
     h.load_genotypes(Gm, S, w1, w2, n1, n2, pos, off)
     for bg in ("per_chrom", "genome"):
@@ -66,15 +61,14 @@ def test_variant_vs_oracle(T, h, knobs, mode, G, n1, n2, S, C, L, W, N):
 
 
 @pytest.mark.parametrize("G", [1, 2])
-@pytest.mark.parametrize("mode", MODES)
-def test_variant_flags_and_inf(T, h, knobs, mode, G):
+def test_variant_flags_and_inf(T, h, knobs, G):
     """Per-SNP flags (spectrum filter bit 0, count_snps filter bit 1) and a precomputed background with empty bins (+inf)."""
     rng = np.random.default_rng(5)
     n1, n2, S = 12, 9, 6000
     Gm, w1, w2, pos, off = random_panel(rng, S, n1, n2, 2, 120000)
     cnt = O.unpack_counts(Gm, w1, w2, n1, n2, S)
     flags = rng.integers(0, 4, size=S).astype(np.uint8)
-    knobs(mode, G)
+    knobs(G)
     h.set_panel(n1, n2, True)
     h.load_counts(cnt.astype(np.uint16), pos, off, flags=flags)
     h.background(T.BG_PER_CHROM)
@@ -117,13 +111,12 @@ def test_variant_flags_and_inf(T, h, knobs, mode, G):
 
 
 @pytest.mark.parametrize("G", [1, 2, 4])
-@pytest.mark.parametrize("mode", MODES)
-def test_variant_exact_zeros(T, h, knobs, mode, G):
+def test_variant_exact_zeros(T, h, knobs, G):
     """Exactly 0.0, bit for bit, where the reference's p_fg == p_bg: (a) windows that are their own background (one window
     per chromosome, per-chromosome background), (b) every SNP in one bin (one-bin background, many windows with N != B)."""
     rng = np.random.default_rng(17)
     n1, n2 = 20, 11
-    knobs(mode, G)
+    knobs(G)
     h.set_panel(n1, n2, True)
     # (a) 5 chromosomes of 60..700 SNPs, one 1 Mb window each
     sizes = [60, 700, 333, 1, 512]
@@ -160,8 +153,8 @@ def test_variant_exact_zeros(T, h, knobs, mode, G):
         assert np.all(exp[a] == 0.0) and np.all(res[a][live] == 0.0), (a, res[a][live])
 
 
-def test_variants_agree_to_rounding(T, h, knobs):
-    """The three kernels compute the same sums in different orders: equal to rounding on the same scan."""
+def test_group_widths_agree_to_rounding(T, h, knobs):
+    """1, 2 and 4 warps per window compute the same sums in different orders: equal to rounding on the same scan."""
     rng = np.random.default_rng(23)
     n1, n2, S = 64, 64, 30000
     Gm, w1, w2, pos, off = random_panel(rng, S, n1, n2, 4, 300000)
@@ -170,12 +163,12 @@ def test_variants_agree_to_rounding(T, h, knobs):
     h.background(T.BG_GENOME)
     h.finalize_background()
     out = {}
-    for mode in MODES:
-        knobs(mode, 1)
-        out[mode] = h.scan(10000)
-    for mode in MODES[1:]:
-        for k, v in out["walk"].items():
+    for G in (1, 2, 4):
+        knobs(G)
+        out[G] = h.scan(10000)
+    for G in (2, 4):
+        for k, v in out[1].items():
             if v.dtype == np.float64:
-                assert np.allclose(out[mode][k], v, rtol=1e-11, atol=1e-11, equal_nan=True), (mode, k)
+                assert np.allclose(out[G][k], v, rtol=1e-11, atol=1e-11, equal_nan=True), (G, k)
             else:
-                assert np.array_equal(out[mode][k], v), (mode, k)
+                assert np.array_equal(out[G][k], v), (G, k)
