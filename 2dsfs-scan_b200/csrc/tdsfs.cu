@@ -518,7 +518,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       p.tile_blocks = 1;
       p.stage_bytes = seg_words * BLK * 4;
       const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
-      p.cwarps = std::min(K1_CWARPS, fit / 2);
+      p.cwarps = std::min(K1_DEFAULT_WARPS, fit / 2);
       p.nstage = p.cwarps * 2;
       p.interleave = 0;
       const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
@@ -529,18 +529,23 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
         p.r0 = ch.r0; p.r1 = ch.r1;
         const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
         const int grid = (int)std::min<long long>(nblk, (long long)c->sm_count);
-        k1_genotypes_wide<<<grid, K1_THREADS, smem, st>>>(p, seg_words);
+        k1_genotypes_wide<<<grid, K1_DEFAULT_WARPS * 32, smem, st>>>(p, seg_words);
         c->launches++;
       }
     } else {
-      p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile: >= one 32-SNP block, ~4-8 KB
+      // Ring geometry (measured, profiles/README.md "K1 ring geometry"): ONE stage per warp and about 128 KB of tiles in
+      // flight per SM.  Rows up to 8 KB per block use two-block tiles; more warps for narrow rows (more per-SNP work per
+      // byte), fewer and larger requests for wide rows.  Deeper rings and more bytes in flight are slower on B200.
+      p.tile_blocks = blk_bytes <= 8192 ? std::max(2, 8192 / blk_bytes) : 1;  // one TMA bulk copy per tile
+      if (const char* e = getenv("TDSFS_K1_TILE")) p.tile_blocks = std::max(1, atoi(e));  // tuning knob: blocks per tile
       p.stage_bytes = p.tile_blocks * blk_bytes;
-      // ring = k stages per consumer warp (k >= 2 when they fit): one being counted, the others in flight from HBM
       const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
-      p.cwarps = std::min(K1_CWARPS, fit);
-      if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(p.cwarps, atoi(e)));  // tuning knob
-      p.nstage = p.cwarps * std::max(1, std::min(4, fit / p.cwarps));  // `depth` stages per warp
+      p.cwarps = std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
+      if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
+      int depth = 1;  // stages per warp
+      if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, std::min(fit / p.cwarps, atoi(e)));  // tuning knob
+      p.nstage = p.cwarps * depth;
       const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
       void (*kern)(KeyParams) = k1_genotypes<0, 0>;
       if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
@@ -556,7 +561,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
         const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
         const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
         const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
-        kern<<<grid, K1_THREADS, smem, st>>>(p);
+        kern<<<grid, p.cwarps * 32, smem, st>>>(p);
         c->launches++;
       }
     }

@@ -19,9 +19,9 @@ namespace tdsfs {
 
 // ------------------------------------------------------------------------------------------------ constants
 constexpr int BLK = 32;               // SNPs per block of the block-transposed genotype layout ("B32")
-constexpr int K1_CWARPS = 12;         // warps of the genotype count kernel (each runs its own TMA ring)
-constexpr int K1_CONS = K1_CWARPS * 32;
-constexpr int K1_THREADS = K1_CONS;
+constexpr int K1_CWARPS = 16;         // most warps the genotype count kernel can run (each runs its own TMA ring)
+constexpr int K1_THREADS = K1_CWARPS * 32;  // launch bound; the launch uses cwarps * 32 threads
+constexpr int K1_DEFAULT_WARPS = 12;
 constexpr int K1_ROWS = 128;          // row granularity of host-side upload chunks (multiple of BLK)
 constexpr int CORNER = 64;            // privatised low-count corner of the 2D background histogram (per CTA, smem)
 constexpr int H1CAP = 2048;           // privatised 1D bins per population (per CTA, smem)
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
     for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
+  for (int i = tid; i < nhist; i += blockDim.x) sm.corner[i] = 0;
   __syncthreads();
 
   // contiguous range of tiles of this CTA; a tile = tile_blocks blocks of 32 SNPs
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes(const __grid_const
     }
   }
   __syncthreads();
-  sink_flush(p, sm, cta_group, tid, K1_THREADS);
+  sink_flush(p, sm, cta_group, tid, blockDim.x);
 }
 
 // Bandwidth probe (TDSFS_K1_PROBE=1, profiling only - produces no spectra): the ring traffic of k1_genotypes without the
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes_wide(const __grid_
     for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < nhist; i += K1_THREADS) sm.corner[i] = 0;
+  for (int i = tid; i < nhist; i += blockDim.x) sm.corner[i] = 0;
   __syncthreads();
   const long long b0 = p.r0 / BLK, b1 = (p.r1 + BLK - 1) / BLK;
   const long long nblk = b1 - b0;
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_genotypes_wide(const __grid_
     }
   }
   __syncthreads();
-  sink_flush(p, sm, cta_group, tid, K1_THREADS);
+  sink_flush(p, sm, cta_group, tid, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------ peer exchange
