@@ -11,19 +11,12 @@ except Exception as e:
     print("${tag} ERR", e)
 PY
 }
-run c5_w12d1t1 config5 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=1
-run c5_w16d1t1 config5 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1
-run c5_w14d1t1 config5 TDSFS_K1_WARPS=14 TDSFS_K1_DEPTH=1
-run c5_w10d1t1 config5 TDSFS_K1_WARPS=10 TDSFS_K1_DEPTH=1
-run c5_w16d1t1_contig config5 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1 TDSFS_K1_INTERLEAVE=0
-run c5_w12d1t2 config5 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=2
-run c5_w8d1t2 config5 TDSFS_K1_WARPS=8 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=2
-run c5_w12d2t1 config5 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=2
-run c4_w12d2t2 config4 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=2
-run c4_w16d1t2 config4 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1
-run c4_w16d2t1 config4 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=2 TDSFS_K1_TILE=1
-run c4_w16d1t3 config4 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=3
-run c4_w16d1t4 config4 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=4
-run c4_w12d1t4 config4 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=4
-run c4_w12d1t3 config4 TDSFS_K1_WARPS=12 TDSFS_K1_DEPTH=1 TDSFS_K1_TILE=3
-run c4_w16d1t2_contig config4 TDSFS_K1_WARPS=16 TDSFS_K1_DEPTH=1 TDSFS_K1_INTERLEAVE=0
+run c5_w6t2 config5 TDSFS_K1_WARPS=6 TDSFS_K1_TILE=2
+run c5_w10t2 config5 TDSFS_K1_WARPS=10 TDSFS_K1_TILE=2
+run c5_w6t3 config5 TDSFS_K1_WARPS=6 TDSFS_K1_TILE=3
+run c5_w5t3 config5 TDSFS_K1_WARPS=5 TDSFS_K1_TILE=3
+run c5_w4t4 config5 TDSFS_K1_WARPS=4 TDSFS_K1_TILE=4
+run c5_w7t2 config5 TDSFS_K1_WARPS=7 TDSFS_K1_TILE=2
+run c5_w8t2_contig config5 TDSFS_K1_WARPS=8 TDSFS_K1_TILE=2 TDSFS_K1_INTERLEAVE=0
+TDSFS_K1_WARPS=6 TDSFS_K1_TILE=3 timeout 60 python -m pytest tests/test_gpu_capi_parity.py -m gpu -x -q -k "genotype_scan_vs_oracle or large_windows" 2>&1 | tail -1
+TDSFS_K1_WARPS=6 TDSFS_K1_TILE=2 timeout 60 python -m pytest tests/test_gpu_capi_parity.py -m gpu -x -q -k "genotype_scan_vs_oracle or large_windows" 2>&1 | tail -1
