@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "tdsfs_kernels.cuh"
+#include "tdsfs_pipeline.cuh"
 
 using namespace tdsfs;
 
@@ -125,6 +126,13 @@ struct tdsfs_ctx {
   unsigned long long* d_work = nullptr;  // window hand-out counter of the scorer (monotonic, never reset)
   unsigned long long work_base = 0;
   bool results_ready = false;
+  // experimental pipelined scorer (TDSFS_PIPELINE=1, tdsfs_pipeline.cuh): window-only sums on a second stream under K1
+  bool pipe = false, pipe_armed = false;
+  long long pipe_W = -1;
+  cudaStream_t score_stream = nullptr;
+  cudaEvent_t ev_chunk[PIPE_MAX_CHUNKS] = {}, ev_scored = nullptr;
+  unsigned long long* d_pipe_work = nullptr;
+  double* d_dxI = nullptr;
   // instrumentation
   cudaEvent_t ev[NEV] = {};
   float ms[8] = {};
@@ -176,7 +184,16 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   tdsfs_ctx* c = new tdsfs_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("TDSFS_PIPELINE")) c->pipe = atoi(e) != 0;
+  if (c->pipe) {
+    // the count kernel's CTAs must be placed before the window-sum CTAs that share their SMs: main stream above the score stream
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, greatest));
+    CK(cudaStreamCreateWithPriority(&c->score_stream, cudaStreamNonBlocking, least));
+  } else {
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  }
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -191,6 +208,15 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   k_ln_int_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_lnI, LN_TABLE);
   c->launches++;
   CK(cudaGetLastError());
+  if (c->pipe) {
+    for (int i = 0; i < PIPE_MAX_CHUNKS; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_scored, cudaEventDisableTiming));
+    CKR(dev_alloc(&c->d_pipe_work, PIPE_MAX_CHUNKS));
+    CKR(dev_alloc(&c->d_dxI, LN_TABLE));
+    k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
@@ -241,6 +267,13 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
   dev_free(c->r_T1b); dev_free(c->r_flags); dev_free(c->d_scratch);
   for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->pipe) {
+    cudaStreamSynchronize(c->score_stream);
+    cudaStreamDestroy(c->score_stream);
+    for (int i = 0; i < PIPE_MAX_CHUNKS; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    if (c->ev_scored) cudaEventDestroy(c->ev_scored);
+    dev_free(c->d_pipe_work); dev_free(c->d_dxI);
+  }
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->plan_stream);
@@ -461,6 +494,10 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   CKR(peer_settle(c));  // peers may still be pushing the previous exchange into the histogram
+  if (c->pipe_armed) {  // window sums of an earlier pass that no scan consumed: let them finish before the records change
+    CK(cudaStreamWaitEvent(st, c->ev_scored, 0));
+    c->pipe_armed = false;
+  }
   CK(cudaEventRecord(c->ev[EV_BG0], st));
   const int NG = mode == TDSFS_BG_PER_CHROM ? c->C : 1;
   c->gstride = (long long)c->bins2d + c->R1 + c->R2;
@@ -554,6 +591,46 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       p.interleave = (p.bg_group == nullptr) ? 1 : 0;
       if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
+      // experimental: K1 in row chunks with the window-only scorer of each chunk on a second stream (tdsfs_pipeline.cuh)
+      const int gwords = score_group_smem_words(c->n1, c->n2);
+      const long long tile_rows = (long long)p.tile_blocks * BLK;
+      int nch = (int)std::min<long long>(PIPE_MAX_CHUNKS, c->S / (4LL << 20));
+      if (const char* e = getenv("TDSFS_PIPELINE_CHUNKS")) nch = std::max(1, std::min(PIPE_MAX_CHUNKS, atoi(e)));
+      const bool pipe = c->pipe && mode == TDSFS_BG_GENOME && p.bg_lo < 0 && c->plan_W > 0 && !c->plan_snp && !c->dFlags &&
+                        c->chunks.size() == 1 && !c->chunks[0].ev && nch >= 2 && kern != k1_probe_ring &&
+                        score_small_ok(c->n1, c->n2, c->bins2d) && SCORE_WARPS * gwords * 4 <= 200 * 1024 && c->S < 0x7FFFFFFFLL;
+      if (pipe) {
+        const long long ncand = c->cand_off_host[c->C];
+        PipeParams q;
+        memset(&q, 0, sizeof q);
+        q.s.rec = c->d_rec; q.s.wlo = c->d_wlo; q.s.whi = c->d_whi; q.s.ncand = ncand;
+        q.s.n1 = c->n1; q.s.n2 = c->n2; q.s.bins2d = c->bins2d; q.s.lnI = c->d_lnI;
+        q.s.r_count = c->r_count; q.s.r_n2 = c->r_n2; q.s.r_n1a = c->r_n1a; q.s.r_n1b = c->r_n1b;
+        q.s.r_T2 = c->r_T2; q.s.r_T1a = c->r_T1a; q.s.r_T1b = c->r_T1b; q.s.r_flags = c->r_flags;
+        q.dxI = c->d_dxI;
+        const int smem3 = SCORE_WARPS * gwords * 4;
+        CK(cudaFuncSetAttribute(k3a_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        CK(cudaMemsetAsync(c->d_pipe_work, 0, sizeof(unsigned long long) * PIPE_MAX_CHUNKS, st));
+        CK(cudaStreamWaitEvent(c->score_stream, c->ev_plan, 0));  // window boundaries (K2 on the plan stream)
+        const long long rows_per = ((c->S + nch - 1) / nch + tile_rows - 1) / tile_rows * tile_rows;
+        int i = 0;
+        for (long long r0 = 0; r0 < c->S; r0 += rows_per, ++i) {
+          p.r0 = r0; p.r1 = std::min<long long>(c->S, r0 + rows_per);
+          const long long ntiles = ((p.r1 - p.r0 + BLK - 1) / BLK + p.tile_blocks - 1) / p.tile_blocks;
+          kern<<<(int)std::min<long long>(ntiles, (long long)c->sm_count), p.cwarps * 32, smem, st>>>(p);
+          CK(cudaEventRecord(c->ev_chunk[i], st));
+          CK(cudaStreamWaitEvent(c->score_stream, c->ev_chunk[i], 0));
+          q.row_lo = (int)p.r0; q.row_hi = (int)p.r1; q.work = c->d_pipe_work + i;
+          // one CTA per SM while a count kernel follows (its CTA + one of these fill an SM's shared memory; more would
+          // keep the next chunk's count CTAs from being placed), every slot for the last chunk
+          const bool last_chunk = p.r1 >= c->S;
+          k3a_window_sums<<<c->sm_count * (last_chunk ? 4 : 1), SCORE_WARPS * 32, smem3, c->score_stream>>>(q);
+          c->launches += 2;
+        }
+        CK(cudaEventRecord(c->ev_scored, c->score_stream));
+        c->pipe_armed = true;
+        c->pipe_W = c->plan_W;
+      } else
       for (auto& ch : c->chunks) {
         if (ch.r1 <= ch.r0) continue;
         if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
@@ -951,7 +1028,20 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     // small windows: groups of G warps per window over shared-memory tables (skipped for panels beyond their limits:
     // K2 then lists every window as "large")
     const int gwords = score_group_smem_words(c->n1, c->n2);
-    if (score_small_ok(c->n1, c->n2, c->bins2d) && gwords * 4 <= 200 * 1024) {
+    const bool armed = c->pipe_armed;
+    if (armed) {  // window sums computed under K1 (tdsfs_pipeline.cuh): wait for them whether or not this scan uses them
+      CK(cudaStreamWaitEvent(st, c->ev_scored, 0));
+      c->pipe_armed = false;
+    }
+    if (armed && planned && !snp_mode && c->pipe_W == W && !c->dFlags && !c->per_chrom_scoring && !c->float_bg) {
+      PipeParams q;
+      memset(&q, 0, sizeof q);
+      q.s = s;
+      q.dxI = c->d_dxI;
+      const int grid = (int)std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * 8);
+      k3b_gather_finish<<<grid, 256, 0, st>>>(q, c->d_large, c->d_nlarge);
+      c->launches++;
+    } else if (score_small_ok(c->n1, c->n2, c->bins2d) && gwords * 4 <= 200 * 1024) {
       // one warp per window when every resident warp gets many windows; two warps per window for small scans
       // (a rank of an 8-GPU run: ~4 windows per warp -> finer granularity evens out the tail; measured 0.135 -> 0.122 ms)
       int G = c->score_group_warps;

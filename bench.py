@@ -273,7 +273,9 @@ def run_b200(args, cfg):
     S_total = cfg["S"] if args.scaling == "strong" else cfg["S"] * world
 
     h = T.Handle(local_rank)
-    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs
+    # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs; above the library's side streams when the
+    # experimental pipelined scorer (TDSFS_PIPELINE=1) needs the count kernel's CTAs placed first
+    stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("TDSFS_PIPELINE", "0") not in ("", "0") else 0)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     h.set_panel(n1, n2, True)
