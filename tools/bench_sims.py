@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: sims_scan replicates, batched.  The SLiM VCFs of the reference are
+not shipped, so the replicates are the survey's synthetic stand-in: G generations x R replicates, n1 = n2 = 5 diploids,
+L = 1.5 Mb, W = 500 kb, SNPs per replicate ~ Poisson(7200) at distinct uniform positions, ancestral frequency log-uniform on
+[1/40, 39/40], population frequencies Balding-Nichols (F = 0.05), genotypes Binomial(2, p), no missing data; per generation the
+background spectra come from the concatenation of its replicates (duplicate 1-POS keys: the last wins) restricted to
+pos <= 500,000, 1D backgrounds unfolded; seeds default_rng(1000 + g*100 + r).
+Reports replicates/s of sims_scan.process_window_batch (one launch per generation), of the per-replicate process_window loop,
+and of the CPU oracle (the reference's algorithm) on a few replicates, and checks the batched results against the oracle.
+usage (GPU box): python tools/bench_sims.py [--generations 4] [--replicates 100] [--oracle-replicates 3] [--cpu-only]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "2dsfs-scan_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+
+N, L, W = 5, 1_500_000, 500_000
+
+
+def replicate(g, r):
+    rng = np.random.default_rng(1000 + g * 100 + r)
+    s = int(rng.poisson(7200))
+    pos = np.sort(rng.choice(np.arange(1, L + 1), size=s, replace=False))
+    f = np.exp(rng.uniform(np.log(1 / 40), np.log(39 / 40), size=s))
+    F = 0.05
+    d = {}
+    alts = []
+    for _pop in range(2):
+        p = rng.beta(f * (1 - F) / F, (1 - f) * (1 - F) / F)
+        alts.append(rng.binomial(2 * N, p))
+    for q, a1, a2 in zip(pos.tolist(), alts[0].tolist(), alts[1].tolist()):
+        d[f"1-{q}"] = {"segregating": ("A", "C"), "context": "-A-", "annotation": "No annotation",
+                       "calls": {"p1": (2 * N - a1, a1), "p2": (2 * N - a2, a2)}}
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--generations", type=int, default=4)
+    ap.add_argument("--replicates", type=int, default=100)
+    ap.add_argument("--oracle-replicates", type=int, default=3)
+    ap.add_argument("--cpu-only", action="store_true", help="generator + oracle only (no GPU): checks the tool itself")
+    args = ap.parse_args()
+    import sfs_oracle as O
+    from helpers import close
+    out = {"config": "sims batch: %d generations x %d replicates, n=5+5, L=1.5 Mb, W=500 kb" % (args.generations, args.replicates)}
+    t_batch = t_loop = t_oracle = 0.0
+    n_oracle = 0
+    snps = 0
+    for g in range(args.generations):
+        dicts = [replicate(g, r) for r in range(args.replicates)]
+        snps += sum(len(d) for d in dicts)
+        concat = {}
+        for d in dicts:
+            concat.update(d)                                   # appended records: the last of a duplicate key wins
+        bg2 = O.calculate_2d_sfs(concat, "p1", "p2", N, N, 0, 500000, None)
+        bg1a = O.calculate_1d_sfs(concat, "p1", N, 0, 500000, None)
+        bg1b = O.calculate_1d_sfs(concat, "p2", N, 0, 500000, None)
+        exp = []
+        t0 = time.perf_counter()
+        for d in dicts[:args.oracle_replicates]:
+            exp.append(O.sims_process_window(d, bg2, bg1a, bg1b, W, "p1", "p2", N, N, None, None, None))
+        t_oracle += time.perf_counter() - t0
+        n_oracle += len(exp)
+        if args.cpu_only:
+            continue
+        import sims_scan as S
+        if g == 0:
+            S.process_window_batch(dicts[:2], bg2, bg1a, bg1b, W, "p1", "p2", N, N, None, None, None)   # warm-up (context, tables)
+        t0 = time.perf_counter()
+        got = S.process_window_batch(dicts, bg2, bg1a, bg1b, W, "p1", "p2", N, N, None, None, None)
+        t_batch += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        one = [S.process_window(d, bg2, bg1a, bg1b, W, "p1", "p2", N, N, None, None, None) for d in dicts]
+        t_loop += time.perf_counter() - t0
+        for e, a, b in zip(exp, got, one):
+            assert list(e) == list(a) == list(b), (list(e), list(a))
+            for k in e:
+                for fld in e[k]:
+                    assert close(a[k][fld], e[k][fld]) and close(b[k][fld], e[k][fld]), (g, k, fld, a[k][fld], e[k][fld])
+    total = args.generations * args.replicates
+    out.update({"replicates": total, "snps": snps, "oracle_cpu_replicates_per_s": n_oracle / t_oracle if t_oracle else None,
+                "oracle_note": "reference algorithm (oracle/sfs_oracle.py sims_process_window), one core, %d replicates timed" % n_oracle})
+    if not args.cpu_only:
+        out.update({"batched_replicates_per_s": total / t_batch, "batched_s": t_batch, "per_replicate_loop_replicates_per_s": total / t_loop,
+                    "per_replicate_loop_s": t_loop, "parity": "first %d replicates of every generation == oracle (1e-9)" % args.oracle_replicates,
+                    "note": "host time includes the dict -> array conversion of every replicate (csrc/dictconv.c)"})
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
