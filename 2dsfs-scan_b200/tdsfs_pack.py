@@ -94,6 +94,18 @@ def _packer():
     return _plib
 
 
+class _PackOwner:
+    """Owns the C++ result of tdsfs_pack_vcf; the numpy views of its arrays keep it alive."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def __del__(self):
+        if self._h:
+            self._lib.tdsfs_pack_free(self._h)
+            self._h = None
+
+
 class PackedPanel:
     """A VCF packed for the GPU: the array form of a data_dict restricted to two populations, at genotype level.
     Accepted by the scanners of LikelihoodInference_jointSFS in place of a data_dict (fast path: no Python dict)."""
@@ -146,32 +158,33 @@ def pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, nthreads=0):
         if "index out of range" in msg:
             raise IndexError(msg)
         raise RuntimeError(msg)
-    try:
-        dims = (_C.c_int64 * 8)()
-        dims2 = (_C.c_int64 * 4)()
-        L.tdsfs_pack_dims(h, dims, dims2)
-        S, W1, W2, ns1, ns2, C, nfix, last = [int(v) for v in dims]
-        P = PackedPanel()
-        P.n, P.W1, P.W2, P.ns1, P.ns2, P.last_key_row = S, W1, W2, ns1, ns2, last
-        P.n_records, P.n_skipped = int(dims2[0]), int(dims2[1])
-        gw = int(dims2[3])
+    owner = _PackOwner(L, h)   # frees the C++ object when the last array that views its memory is gone
+    dims = (_C.c_int64 * 8)()
+    dims2 = (_C.c_int64 * 4)()
+    L.tdsfs_pack_dims(h, dims, dims2)
+    S, W1, W2, ns1, ns2, C, nfix, last = [int(v) for v in dims]
+    P = PackedPanel()
+    P.n, P.W1, P.W2, P.ns1, P.ns2, P.last_key_row = S, W1, W2, ns1, ns2, last
+    P.n_records, P.n_skipped = int(dims2[0]), int(dims2[1])
+    gw = int(dims2[3])
 
-        def arr(ptr, n, dt):
-            if n == 0:
-                return np.zeros(0, dtype=dt)
-            return np.ctypeslib.as_array(_C.cast(ptr, _C.POINTER(_C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+    def view(ptr, n, dt):
+        """zero-copy numpy view of the packer's memory (the 2-bit matrix of a large VCF is the size of host RAM budgets)"""
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (_C.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(ptr)
+        buf._owner = owner
+        return np.frombuffer(buf, dtype=dt)
 
-        P.G = arr(L.tdsfs_pack_genotypes(h), gw, np.uint32)
-        P.pos = arr(L.tdsfs_pack_positions(h), S, np.int32).astype(np.int64)
-        P.off = arr(L.tdsfs_pack_chrom_off(h), C + 1, np.int64)
-        names = L.tdsfs_pack_chrom_names(h).decode()
-        P.chroms = names.split("\n")[:-1] if names else []
-        vocab = L.tdsfs_pack_ann_vocab(h).decode().split("\n")[:-1]
-        codes = arr(L.tdsfs_pack_ann_codes(h), S, np.int32)
-        P.ann = np.array(vocab, dtype=object)[codes] if S else np.array([], dtype=object)
-        fix_dt = np.dtype([("snp", "<i8"), ("pop", "<i4"), ("dref", "<i4"), ("dalt", "<i4")], align=True)
-        P.fixups = arr(L.tdsfs_pack_fixups(h), nfix, fix_dt) if nfix else None
-        P.pops = (pop1, pop2)
-        return P
-    finally:
-        L.tdsfs_pack_free(h)
+    P.G = view(L.tdsfs_pack_genotypes(h), gw, np.uint32)
+    P.pos = view(L.tdsfs_pack_positions(h), S, np.int32).astype(np.int64)
+    P.off = view(L.tdsfs_pack_chrom_off(h), C + 1, np.int64).copy()
+    names = L.tdsfs_pack_chrom_names(h).decode()
+    P.chroms = names.split("\n")[:-1] if names else []
+    vocab = L.tdsfs_pack_ann_vocab(h).decode().split("\n")[:-1]
+    codes = view(L.tdsfs_pack_ann_codes(h), S, np.int32)
+    P.ann = np.array(vocab, dtype=object)[codes] if S else np.array([], dtype=object)
+    fix_dt = np.dtype([("snp", "<i8"), ("pop", "<i4"), ("dref", "<i4"), ("dalt", "<i4")], align=True)
+    P.fixups = view(L.tdsfs_pack_fixups(h), nfix, fix_dt).copy() if nfix else None
+    P.pops = (pop1, pop2)
+    return P
