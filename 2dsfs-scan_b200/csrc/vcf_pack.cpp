@@ -23,6 +23,7 @@
 #include <future>
 #include <mutex>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -362,6 +363,88 @@ struct Input {
   }
 };
 
+// ---------------------------------------------------------------------------------------------- counts mode
+// make_data_dict_vcf itself (reference :36-138): every population of the popmap, per-record (ref, alt) counts, the key text
+// "CHROM-POS" as written, REF/ALT, annotation.  The Python side (tdsfs_pack.vcf_counts) turns the arrays into the dict.
+struct CRec {
+  std::string key, ann, err;
+  char ref = 0, alt = 0;
+  int ncols = 0;          // zipped sample columns of this record: populations first seen at a later column get no entry
+  bool ok = false;
+};
+
+struct CountsOut {
+  int64_t n = 0;
+  int npop = 0;
+  std::string pop_blob, keys_blob, vocab_blob, refalt;
+  std::vector<int64_t> key_off;
+  std::vector<int32_t> first_col, ann_code, cnt, ncols;
+};
+
+void parse_line_counts(const char* s, size_t n, const std::vector<int>& col_pop, int npop, CRec& r, int32_t* cnt) {
+  const char* end = s + n;
+  std::pair<const char*, size_t> cols[9];
+  const char* q = s;
+  int nc = 0;
+  bool more = false;
+  while (nc < 9) {
+    const char* t = (const char*)memchr(q, '\t', (size_t)(end - q));
+    cols[nc++] = {q, (size_t)((t ? t : end) - q)};
+    if (!t) { q = end; break; }
+    q = t + 1;
+    if (nc == 9) more = true;
+  }
+  if (nc < 8) { r.err = "list index out of range (record with fewer than 8 columns)"; return; }
+  static thread_local std::vector<std::pair<const char*, size_t>> sub;
+  split_char(cols[7].first, cols[7].second, '|', sub);
+  r.ann = sub.size() >= 2 ? std::string(sub[1].first, sub[1].second) : "No annotation";
+  if (!(cols[6].second == 4 && memcmp(cols[6].first, "PASS", 4) == 0) && !(cols[6].second == 1 && cols[6].first[0] == '.')) return;
+  auto base = [](const std::pair<const char*, size_t>& c) -> char {
+    if (c.second != 1) return 0;
+    const char u = (char)toupper((unsigned char)c.first[0]);
+    return (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? u : 0;
+  };
+  r.ref = base(cols[3]);
+  r.alt = base(cols[4]);
+  if (!r.ref || !r.alt) return;
+  if (nc < 9) { r.err = "list index out of range (record without a FORMAT column)"; return; }
+  split_char(cols[8].first, cols[8].second, ':', sub);
+  int gti = -1;
+  for (size_t i = 0; i < sub.size(); ++i)
+    if (sub[i].second == 2 && sub[i].first[0] == 'G' && sub[i].first[1] == 'T') { gti = (int)i; break; }
+  if (gti < 0) { r.err = "'GT' is not in list"; return; }
+  r.key.assign(cols[0].first, cols[0].second);
+  r.key.push_back('-');
+  r.key.append(cols[1].first, cols[1].second);
+  for (int p = 0; p < 2 * npop; ++p) cnt[p] = 0;
+  const size_t nplan = col_pop.size();
+  for (size_t j = 0; more && j < nplan; ++j) {
+    const char* g = q;
+    for (int k = 0; k < gti; ++k) {
+      while (g < end && *g != ':' && *g != '\t') ++g;
+      if (g == end || *g == '\t') { r.err = "list index out of range (sample without GT sub-field)"; return; }
+      ++g;
+    }
+    int ref = 0, alt = 0;
+    for (const char* f = g; g < end && *g != ':' && *g != '\t'; ++g) {
+      if (((g - f) & 1) == 0) {  // gt[::2]
+        ref += *g == '0';
+        alt += *g == '1';
+      }
+    }
+    cnt[2 * col_pop[j]] += ref;
+    cnt[2 * col_pop[j] + 1] += alt;
+    r.ncols = (int)j + 1;
+    if (g < end && *g != '\t') {
+      const char* t = (const char*)memchr(g, '\t', (size_t)(end - g));
+      g = t ? t : end;
+    }
+    if (g == end) break;
+    q = g + 1;
+  }
+  r.ok = true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -569,5 +652,163 @@ const int32_t* tdsfs_pack_ann_codes(void* h) { return ((Packed*)h)->ann_code.dat
 const void* tdsfs_pack_fixups(void* h) { return ((Packed*)h)->fix.data(); }  // {int64 snp; int32 pop, dref, dalt} = tdsfs_fixup_t
 const char* tdsfs_pack_chrom_names(void* h) { return ((Packed*)h)->names_blob.c_str(); }   // '\n'-separated
 const char* tdsfs_pack_ann_vocab(void* h) { return ((Packed*)h)->vocab_blob.c_str(); }
+
+
+// ---- counts mode (make_data_dict_vcf): opaque handle, NULL on error
+void* tdsfs_vcf_counts(const char* vcf_path, const char* popmap_path, int nthreads) {
+  try {
+    std::unordered_map<std::string, std::string> popmap;
+    {
+      FILE* f = fopen(popmap_path, "r");
+      if (!f) { g_err = std::string("cannot open popmap ") + popmap_path; return nullptr; }
+      char* line = nullptr; size_t cap = 0; ssize_t n;
+      std::vector<std::pair<const char*, size_t>> cols;
+      while ((n = getline(&line, &cap, f)) >= 0) {
+        std::string s = strip(std::string(line, (size_t)n));
+        split_char(s.data(), s.size(), '\t', cols);
+        if (cols.size() >= 2) popmap[std::string(cols[0].first, cols[0].second)] = std::string(cols[1].first, cols[1].second);
+      }
+      free(line);
+      fclose(f);
+    }
+    if (nthreads <= 0) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      nthreads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+      nthreads = std::max(1, nthreads);
+    }
+    Pool parse_pool(nthreads), inflate_pool(std::max(1, nthreads / 2));
+    Input in;
+    in.pool = &inflate_pool;
+    if (!in.open(vcf_path, nthreads)) { g_err = std::string("cannot open VCF ") + vcf_path; return nullptr; }
+
+    std::vector<int> col_pop;                       // positional population list (:81-85), as indices into `pops`
+    std::vector<std::string> pops;                  // distinct labels in order of first appearance
+    std::vector<int32_t> first_col;
+    std::unordered_map<std::string, int> pop_id;
+    CountsOut* P = new CountsOut();
+    std::unique_ptr<CountsOut> guard(P);
+    std::map<std::string, int> vocab;
+    std::vector<std::string> vocab_list;
+    std::vector<std::pair<const char*, size_t>> batch;
+    std::vector<CRec> recs;
+    std::vector<int32_t> cw;
+    // records parsed with fewer populations than the final count are padded at the end (a header after records adds labels)
+    std::vector<int> rec_npop;
+    std::string first_err;
+    auto flush = [&]() {
+      if (batch.empty()) return;
+      const size_t np2 = 2 * pops.size();
+      recs.assign(batch.size(), CRec());
+      cw.assign(batch.size() * std::max<size_t>(np2, 1), 0);
+      const int nt = (int)std::min<size_t>((size_t)nthreads, (batch.size() + 63) / 64);
+      parse_pool.run(nt, [&](int t) {
+        const size_t a = batch.size() * (size_t)t / (size_t)nt, b = batch.size() * (size_t)(t + 1) / (size_t)nt;
+        for (size_t i = a; i < b; ++i) parse_line_counts(batch[i].first, batch[i].second, col_pop, (int)pops.size(), recs[i], cw.data() + i * np2);
+      });
+      for (size_t i = 0; i < recs.size(); ++i) {
+        CRec& r = recs[i];
+        if (!r.err.empty()) { if (first_err.empty()) first_err = r.err; break; }  // the reference raises at this record
+        if (!r.ok) continue;
+        P->key_off.push_back((int64_t)P->keys_blob.size());
+        P->keys_blob += r.key;
+        P->refalt.push_back(r.ref);
+        P->refalt.push_back(r.alt);
+        auto it = vocab.find(r.ann);
+        if (it == vocab.end()) { it = vocab.emplace(r.ann, (int)vocab_list.size()).first; vocab_list.push_back(r.ann); }
+        P->ann_code.push_back(it->second);
+        P->ncols.push_back(r.ncols);
+        P->cnt.insert(P->cnt.end(), cw.begin() + (long)(i * np2), cw.begin() + (long)((i + 1) * np2));
+        rec_npop.push_back((int)pops.size());
+        ++P->n;
+      }
+      batch.clear();
+    };
+    std::string chunk, next;
+    bool have = in.next_chunk(chunk);
+    while (have && first_err.empty()) {
+      std::future<bool> more = std::async(std::launch::async, [&]() { return in.next_chunk(next); });
+      const char* p = chunk.data();
+      const char* end = p + chunk.size();
+      while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl + 1 : end;
+        const size_t n = (size_t)(le - p);
+        if (n >= 2 && p[0] == '#' && p[1] == '#') { p = le; continue; }
+        if (n >= 1 && p[0] == '#') {
+          flush();
+          const std::string line(p, n);
+          size_t i = 0; int col = 0;
+          while (i < line.size()) {
+            size_t a = line.find_first_not_of(WS, i);
+            if (a == std::string::npos) break;
+            size_t b = line.find_first_of(WS, a);
+            if (b == std::string::npos) b = line.size();
+            if (col >= 9) {
+              auto it = popmap.find(line.substr(a, b - a));
+              if (it != popmap.end()) {
+                auto pi = pop_id.find(it->second);
+                if (pi == pop_id.end()) {
+                  pi = pop_id.emplace(it->second, (int)pops.size()).first;
+                  pops.push_back(it->second);
+                  first_col.push_back((int32_t)col_pop.size());
+                }
+                col_pop.push_back(pi->second);
+              }
+            }
+            ++col; i = b;
+          }
+          p = le;
+          continue;
+        }
+        batch.emplace_back(p, n);
+        p = le;
+      }
+      flush();
+      have = more.get();
+      chunk.swap(next);
+    }
+    in.close();
+    if (!first_err.empty()) { g_err = first_err; return nullptr; }
+    if (!in.err.empty()) { g_err = "reading VCF: " + in.err; return nullptr; }
+    // uniform [n][npop][2] layout: records parsed before a later header line knew fewer populations
+    P->npop = (int)pops.size();
+    bool ragged = false;
+    for (int v : rec_npop) ragged = ragged || v != P->npop;
+    if (ragged) {
+      std::vector<int32_t> full((size_t)P->n * 2 * (size_t)P->npop, 0);
+      size_t o = 0;
+      for (int64_t i = 0; i < P->n; ++i) {
+        const size_t w = 2 * (size_t)rec_npop[(size_t)i];
+        std::copy(P->cnt.begin() + (long)o, P->cnt.begin() + (long)(o + w), full.begin() + (long)((size_t)i * 2 * (size_t)P->npop));
+        o += w;
+      }
+      P->cnt.swap(full);
+    }
+    P->key_off.push_back((int64_t)P->keys_blob.size());
+    P->first_col = first_col;
+    for (auto& c : pops) { P->pop_blob += c; P->pop_blob.push_back('\n'); }
+    for (auto& c : vocab_list) { P->vocab_blob += c; P->vocab_blob.push_back('\n'); }
+    return guard.release();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void tdsfs_vcf_counts_free(void* h) { delete (CountsOut*)h; }
+// dims[4] = n records, n populations, bytes of the key blob, n vocabulary entries
+void tdsfs_vcf_counts_dims(void* h, int64_t* dims) {
+  CountsOut* P = (CountsOut*)h;
+  dims[0] = P->n; dims[1] = P->npop; dims[2] = (int64_t)P->keys_blob.size(); dims[3] = (int64_t)P->first_col.size();
+}
+const char* tdsfs_vcf_counts_keys(void* h) { return ((CountsOut*)h)->keys_blob.data(); }
+const int64_t* tdsfs_vcf_counts_key_off(void* h) { return ((CountsOut*)h)->key_off.data(); }
+const char* tdsfs_vcf_counts_refalt(void* h) { return ((CountsOut*)h)->refalt.data(); }
+const int32_t* tdsfs_vcf_counts_ann_codes(void* h) { return ((CountsOut*)h)->ann_code.data(); }
+const int32_t* tdsfs_vcf_counts_cnt(void* h) { return ((CountsOut*)h)->cnt.data(); }
+const int32_t* tdsfs_vcf_counts_ncols(void* h) { return ((CountsOut*)h)->ncols.data(); }
+const int32_t* tdsfs_vcf_counts_first_col(void* h) { return ((CountsOut*)h)->first_col.data(); }
+const char* tdsfs_vcf_counts_pops(void* h) { return ((CountsOut*)h)->pop_blob.c_str(); }
+const char* tdsfs_vcf_counts_vocab(void* h) { return ((CountsOut*)h)->vocab_blob.c_str(); }
 
 }  // extern "C"

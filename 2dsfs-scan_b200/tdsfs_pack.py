@@ -90,6 +90,16 @@ def _packer():
             getattr(L, f).argtypes = [_C.c_void_p]
         L.tdsfs_pack_dims.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
         L.tdsfs_pack_free.argtypes = [_C.c_void_p]
+        L.tdsfs_vcf_counts.restype = _C.c_void_p
+        L.tdsfs_vcf_counts.argtypes = [_C.c_char_p, _C.c_char_p, _C.c_int]
+        L.tdsfs_vcf_counts_free.argtypes = [_C.c_void_p]
+        L.tdsfs_vcf_counts_dims.argtypes = [_C.c_void_p, _C.c_void_p]
+        for f in ("keys", "key_off", "refalt", "ann_codes", "cnt", "ncols", "first_col"):
+            getattr(L, "tdsfs_vcf_counts_" + f).restype = _C.c_void_p
+            getattr(L, "tdsfs_vcf_counts_" + f).argtypes = [_C.c_void_p]
+        for f in ("pops", "vocab"):
+            getattr(L, "tdsfs_vcf_counts_" + f).restype = _C.c_char_p
+            getattr(L, "tdsfs_vcf_counts_" + f).argtypes = [_C.c_void_p]
         _plib = L
     return _plib
 
@@ -188,3 +198,57 @@ def pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, nthreads=0):
     P.fixups = view(L.tdsfs_pack_fixups(h), nfix, fix_dt).copy() if nfix else None
     P.pops = (pop1, pop2)
     return P
+
+
+def _raise_pack_error(msg):
+    if "cannot open" in msg:
+        raise FileNotFoundError(msg)
+    if "not in list" in msg or "invalid literal" in msg:
+        raise ValueError(msg)
+    if "index out of range" in msg:
+        raise IndexError(msg)
+    raise RuntimeError(msg)
+
+
+def vcf_to_data_dict(vcf_filename, popinfo_filename, nthreads=0):
+    """make_data_dict_vcf (reference :36-138) with the text work in C++ (csrc/vcf_pack.cpp, counts mode: gzip or BGZF, parsed
+    in parallel); only the construction of the dict itself stays in Python.  Same dict, same exception types."""
+    L = _packer()
+    h = L.tdsfs_vcf_counts(str(vcf_filename).encode(), str(popinfo_filename).encode(), int(nthreads))
+    if not h:
+        _raise_pack_error(L.tdsfs_pack_last_error().decode())
+    try:
+        dims = (_C.c_int64 * 4)()
+        L.tdsfs_vcf_counts_dims(h, dims)
+        n, npop, key_bytes = int(dims[0]), int(dims[1]), int(dims[2])
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer((_C.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt)
+
+        pops = L.tdsfs_vcf_counts_pops(h).decode().split("\n")[:-1]
+        vocab = L.tdsfs_vcf_counts_vocab(h).decode().split("\n")[:-1]
+        blob = _C.string_at(L.tdsfs_vcf_counts_keys(h), key_bytes).decode() if key_bytes else ""
+        off = arr(L.tdsfs_vcf_counts_key_off(h), n + 1, np.int64).tolist()
+        refalt = _C.string_at(L.tdsfs_vcf_counts_refalt(h), 2 * n).decode() if n else ""
+        ann = arr(L.tdsfs_vcf_counts_ann_codes(h), n, np.int32).tolist()
+        ncols = arr(L.tdsfs_vcf_counts_ncols(h), n, np.int32).tolist()
+        first = arr(L.tdsfs_vcf_counts_first_col(h), npop, np.int32).tolist()
+        cnt = arr(L.tdsfs_vcf_counts_cnt(h), n * npop * 2, np.int32).reshape(n, npop, 2).tolist() if n and npop else [[] for _ in range(n)]
+        # a population enters calls_dict when its first zipped column is reached (:118-130); insertion order = first appearance
+        order = sorted(range(npop), key=lambda p: first[p])
+        full = max(first) + 1 if first else 0
+        data_dict = {}
+        for i in range(n):
+            ref, alt = refalt[2 * i], refalt[2 * i + 1]
+            c, nc = cnt[i], ncols[i]
+            if nc >= full:
+                calls = {pops[p]: (c[p][0], c[p][1]) for p in order}
+            else:
+                calls = {pops[p]: (c[p][0], c[p][1]) for p in order if first[p] < nc}
+            data_dict[blob[off[i]:off[i + 1]]] = {"segregating": (ref, alt), "context": "-" + ref + "-", "calls": calls,
+                                                  "annotation": vocab[ann[i]]}
+        return data_dict
+    finally:
+        L.tdsfs_vcf_counts_free(h)

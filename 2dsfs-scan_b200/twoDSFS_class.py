@@ -33,7 +33,15 @@ def parse_vcf_to_dict(vcf_filename, popinfo_filename):
     """Host-side ingest with the reference's exact gates (make_data_dict_vcf, reference :36-138): FILTER in {PASS, .},
     single-base A/C/G/T REF and ALT, annotation = 2nd '|' field of INFO, per-sample counting of the characters '0'/'1'
     at even offsets of the GT sub-field, and the positional population list (header samples found in the popmap, in
-    order, zipped with the sample columns)."""
+    order, zipped with the sample columns).  The text work runs in the C++ packer (tdsfs_pack.vcf_to_data_dict) when its
+    library is built; the Python loop below is the same algorithm and the cross-check of the tests."""
+    import tdsfs_pack
+    if os.path.exists(tdsfs_pack._PACK_LIB) and not os.environ.get("TDSFS_PY_INGEST"):
+        return tdsfs_pack.vcf_to_data_dict(vcf_filename, popinfo_filename)
+    return _parse_vcf_to_dict_py(vcf_filename, popinfo_filename)
+
+
+def _parse_vcf_to_dict_py(vcf_filename, popinfo_filename):
     popmap = {}
     with open(popinfo_filename, "r") as f:
         for line in f:

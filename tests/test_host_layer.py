@@ -22,6 +22,15 @@ def test_parse_ecb_subset_counts():
     assert [[k, list(v["calls"]["uv"]), list(v["calls"]["bv"])] for k, v in d.items()] == exp["counts"]
 
 
+def test_cpp_and_python_ingest_agree():
+    """parse_vcf_to_dict runs the text work in C++ (counts mode of csrc/vcf_pack.cpp); the Python loop is the same algorithm."""
+    import twoDSFS_class as K
+    for stem in ("ingest_small", "ecb_subset"):
+        args = (os.path.join(GOLDEN, stem + ".vcf.gz"), os.path.join(GOLDEN, stem + ".popmap.txt"))
+        a, b = K.parse_vcf_to_dict(*args), K._parse_vcf_to_dict_py(*args)
+        assert a == b and list(a) == list(b) and all(list(a[k]["calls"]) == list(b[k]["calls"]) for k in a)
+
+
 def test_snp_table_sorting_and_flags():
     from tdsfs_engine import SnpTable, filter_flags
     d = {"chr2-50": {"calls": {"a": (3, 1), "b": (2, 2)}, "annotation": "x"},

@@ -71,6 +71,12 @@ def test_packer_matches_oracle_ingest(tmp_path, seed, container):
         write_bgzf(text.encode(), vcf, block=int(rng.choice([300, 4096, 65280])))
         assert gzip.open(vcf, "rb").read() == text.encode()
     d = O.make_data_dict_vcf(vcf, pm)
+    # counts mode: make_data_dict_vcf itself (all populations, key text, REF/ALT, annotation), dict and orders identical
+    from tdsfs_pack import vcf_to_data_dict
+    dd = vcf_to_data_dict(vcf, pm, nthreads=int(rng.choice([1, 3, 8])))
+    assert dd == d and list(dd) == list(d)
+    assert all(list(dd[k]["calls"]) == list(d[k]["calls"]) for k in d)
+    assert all(type(v) is int for k in list(d)[:50] for c in dd[k]["calls"].values() for v in c)
     P = pack_vcf(vcf, pm, "uv", "bv", nthreads=int(rng.choice([1, 2, 5])))
     keys = [f"{P.chroms[c]}-{p}" for c in range(len(P.chroms)) for p in P.pos[P.off[c]:P.off[c + 1]].tolist()]
     assert keys == sorted(d, key=lambda k: (k.split("-")[0], int(k.split("-")[1])))
@@ -82,8 +88,27 @@ def test_packer_matches_oracle_ingest(tmp_path, seed, container):
     assert P.n_records - P.n_skipped >= P.n                     # duplicates collapse
 
 
+def test_counts_mode_second_header_and_ragged_records(tmp_path):
+    """A header line after records extends the positional population list (:78-85); short records leave later populations
+    out of their calls dict (:118)."""
+    from tdsfs_pack import vcf_to_data_dict
+    pm = str(tmp_path / "popmap.txt")
+    open(pm, "w").write("a\tuv\nb\tbv\nc\tzz\nd\tuv\n")
+    head = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    text = (head + "a\tb\n" + "c1\t5\t.\tA\tC\t.\tPASS\tx|syn\tGT\t0|1\t1|1\n" + "c1\t9\t.\tg\tt\t.\t.\t.\tGT\t0|1\n" +
+            head + "c\td\n" + "c1\t07\t.\tA\tC\t.\tPASS\t.\tGT:DP\t0|1:3\t1|1:2\t0/0:1\t./1:9\n" +
+            "c1\t5\t.\tA\tG\t.\tPASS\t.\tGT\t1|1\t0|0\t0|1")
+    vcf = str(tmp_path / "h.vcf.gz")
+    with gzip.open(vcf, "wt") as f:
+        f.write(text)
+    d = O.make_data_dict_vcf(vcf, pm)
+    dd = vcf_to_data_dict(vcf, pm)
+    assert dd == d and list(dd) == list(d) and [list(v["calls"]) for v in dd.values()] == [list(v["calls"]) for v in d.values()]
+    assert dd["c1-07"]["calls"] == {"uv": (1, 2), "bv": (0, 2), "zz": (2, 0)} and dd["c1-5"]["segregating"] == ("A", "G")
+
+
 def test_packer_errors(tmp_path):
-    from tdsfs_pack import pack_vcf
+    from tdsfs_pack import pack_vcf, vcf_to_data_dict
     pm = str(tmp_path / "popmap.txt")
     open(pm, "w").write("a\tuv\nb\tbv\n")
     head = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n"
@@ -97,5 +122,16 @@ def test_packer_errors(tmp_path):
             O.make_data_dict_vcf(vcf, pm)
         with pytest.raises(exc):
             pack_vcf(vcf, pm, "uv", "bv")
+        with pytest.raises(exc):
+            vcf_to_data_dict(vcf, pm)
+    vcf = str(tmp_path / "short.vcf.gz")
+    with gzip.open(vcf, "wt") as f:
+        f.write(head + "c\t5\t.\tA\tC\t.\tPASS\n")                                   # cols[7] (:92)
+    with pytest.raises(IndexError):
+        O.make_data_dict_vcf(vcf, pm)
+    with pytest.raises(IndexError):
+        vcf_to_data_dict(vcf, pm)
+    with pytest.raises(FileNotFoundError):
+        vcf_to_data_dict(str(tmp_path / "missing.vcf.gz"), pm)
     with pytest.raises(FileNotFoundError):
         pack_vcf(str(tmp_path / "missing.vcf.gz"), pm, "uv", "bv")
