@@ -10,11 +10,11 @@
 #include <vector>
 
 #include "tdsfs_kernels.cuh"
-#include "tdsfs_pipeline.cuh"
+#include "tdsfs_fused.cuh"
 
 using namespace tdsfs;
 
-#define TDSFS_VERSION 100
+#define TDSFS_VERSION 200
 
 static thread_local std::string g_err;
 
@@ -75,9 +75,19 @@ struct tdsfs_ctx {
   long long* d_off = nullptr;
   std::vector<Chunk> chunks;
   // keys
-  uint2* d_rec = nullptr;  // per-SNP (2D bin, raw alt pair)
+  void* d_rec = nullptr;   // per-SNP records (RecFmt: 4-byte narrow or 8-byte wide)
   long long key_cap = 0;
   bool keys_ready = false;
+  RecFmt fmt = {0, 0, 0, 0};  // format of the records d_rec currently holds
+  bool force_wide = false;    // a SNP did not fit the narrow record: wide records until the next load
+  // fused scan: window sums written by k1_fused for the plan (fused_W, fused_snp)
+  double* d_ws = nullptr;
+  long long ws_cap = 0;
+  long long fused_W = -1;
+  int fused_snp = -1;
+  bool ws_ready = false;
+  bool last_fused = false;    // the last scan was finished by k3_finish
+  double* d_dxI = nullptr;
   // background
   int bg_mode = -1, NG = 0;
   long long gstride = 0;
@@ -126,13 +136,6 @@ struct tdsfs_ctx {
   unsigned long long* d_work = nullptr;  // window hand-out counter of the scorer (monotonic, never reset)
   unsigned long long work_base = 0;
   bool results_ready = false;
-  // experimental pipelined scorer (TDSFS_PIPELINE=1, tdsfs_pipeline.cuh): window-only sums on a second stream under K1
-  bool pipe = false, pipe_armed = false;
-  long long pipe_W = -1;
-  cudaStream_t score_stream = nullptr;
-  cudaEvent_t ev_chunk[PIPE_MAX_CHUNKS] = {}, ev_scored = nullptr;
-  unsigned long long* d_pipe_work = nullptr;
-  double* d_dxI = nullptr;
   // instrumentation
   cudaEvent_t ev[NEV] = {};
   float ms[8] = {};
@@ -162,6 +165,18 @@ static bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// device-side error word -> return code (bit0 range, bit2 peer timeout, bit3 narrow-record overflow)
+static int deferred_error(tdsfs_ctx* c, int err) {
+  if (err & 4) return fail(TDSFS_ERR_CUDA, "peer exchange: a rank did not reach the barrier in time; the background is incomplete");
+  if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
+  if (err & 8) {
+    c->force_wide = true;
+    c->ws_ready = false;
+    return fail(TDSFS_ERR_RETRY, "a SNP's missing-call counts do not fit the 4-byte record; the handle now uses 8-byte records: run the pass again");
+  }
+  return 0;
+}
+
 static int finish(tdsfs_ctx* c) {
   if (c->sync) CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -184,16 +199,7 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   tdsfs_ctx* c = new tdsfs_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (const char* e = getenv("TDSFS_PIPELINE")) c->pipe = atoi(e) != 0;
-  if (c->pipe) {
-    // the count kernel's CTAs must be placed before the window-sum CTAs that share their SMs: main stream above the score stream
-    int least = 0, greatest = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    CK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, greatest));
-    CK(cudaStreamCreateWithPriority(&c->score_stream, cudaStreamNonBlocking, least));
-  } else {
-    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  }
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -208,15 +214,10 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   k_ln_int_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_lnI, LN_TABLE);
   c->launches++;
   CK(cudaGetLastError());
-  if (c->pipe) {
-    for (int i = 0; i < PIPE_MAX_CHUNKS; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_scored, cudaEventDisableTiming));
-    CKR(dev_alloc(&c->d_pipe_work, PIPE_MAX_CHUNKS));
-    CKR(dev_alloc(&c->d_dxI, LN_TABLE));
-    k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
-    c->launches++;
-    CK(cudaGetLastError());
-  }
+  CKR(dev_alloc(&c->d_dxI, LN_TABLE));
+  k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
+  c->launches++;
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
@@ -246,6 +247,8 @@ static void free_data(tdsfs_ctx* c) {
   c->cand_W = -1;
   c->groups_mode = -1;
   c->plan_W = -1;
+  c->ws_ready = false;
+  c->force_wide = false;
 }
 
 extern "C" void tdsfs_destroy(tdsfs_t* c) {
@@ -260,20 +263,15 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   peer_unmap(c);
   dev_free(c->d_peer_flags);
   dev_free(c->d_work);
-  dev_free(c->d_rec); dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
+  if (c->d_rec) cudaFree(c->d_rec);
+  dev_free(c->d_hist); dev_free(c->d_bg_group); dev_free(c->d_score_group);
   dev_free(c->d_lb2); dev_free(c->d_lb1a); dev_free(c->d_lb1b); dev_free(c->d_B); dev_free(c->d_Bsum); dev_free(c->d_lnI);
   dev_free(c->d_err); dev_free(c->d_cand_off); dev_free(c->d_wlo); dev_free(c->d_whi); dev_free(c->d_wchrom);
   dev_free(c->d_large); dev_free(c->d_wstart); dev_free(c->d_wend); dev_free(c->d_nlarge);
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
   dev_free(c->r_T1b); dev_free(c->r_flags); dev_free(c->d_scratch);
   for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  if (c->pipe) {
-    cudaStreamSynchronize(c->score_stream);
-    cudaStreamDestroy(c->score_stream);
-    for (int i = 0; i < PIPE_MAX_CHUNKS; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
-    if (c->ev_scored) cudaEventDestroy(c->ev_scored);
-    dev_free(c->d_pipe_work); dev_free(c->d_dxI);
-  }
+  dev_free(c->d_dxI); dev_free(c->d_ws);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->plan_stream);
@@ -297,7 +295,7 @@ extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold)
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
   if (n1 < 1 || n2 < 1 || n1 > 32767 || n2 > 32767) return fail(TDSFS_ERR_ARG, "panel sizes must be in [1, 32767] (got %d, %d)", n1, n2);
   long long bins = (long long)(2 * n1 + 1) * (2 * n2 + 1);
-  if (bins >= 0xFFFFFFFFLL) return fail(TDSFS_ERR_ARG, "2D spectrum too large");
+  if (bins > 0x7FFFFFFFLL) return fail(TDSFS_ERR_ARG, "2D spectrum too large: (2 n1 + 1)(2 n2 + 1) = %lld bins exceeds 2^31 - 1", bins);
   CK(cudaSetDevice(c->device));
   c->n1 = n1; c->n2 = n2; c->fold = fold != 0;
   c->R1 = 2 * n1 + 1; c->R2 = 2 * n2 + 1; c->bins2d = (int)bins;
@@ -369,8 +367,9 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
       }
   }
   if (S > c->key_cap) {
-    dev_free(c->d_rec);
-    CKR(dev_alloc(&c->d_rec, S));
+    if (c->d_rec) cudaFree(c->d_rec);
+    c->d_rec = nullptr;
+    CK(cudaMalloc(&c->d_rec, (size_t)std::max<long long>(S, 1) * sizeof(uint2)));  // sized for the wide form
     c->key_cap = S;
   }
   return 0;
@@ -444,7 +443,9 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
     uint32_t* d = (uint32_t*)dv;
     c->dG = d;
     c->own_G = true;
-    const long long blks_per_chunk = std::max<long long>(K1_ROWS / BLK, (64LL << 20) / blk_bytes / (K1_ROWS / BLK) * (K1_ROWS / BLK));
+    long long chunk_bytes = 64LL << 20;
+    if (const char* e = getenv("TDSFS_UPLOAD_CHUNK_KB")) chunk_bytes = std::max(1, atoi(e)) * 1024LL;  // test knob: many small chunks
+    const long long blks_per_chunk = std::max<long long>(K1_ROWS / BLK, chunk_bytes / blk_bytes / (K1_ROWS / BLK) * (K1_ROWS / BLK));
     CK(cudaStreamSynchronize(c->stream));
     for (long long bb0 = 0; bb0 < nblk; bb0 += blks_per_chunk) {
       const long long bb1 = std::min<long long>(nblk, bb0 + blks_per_chunk);
@@ -480,7 +481,7 @@ static void fill_key_params(tdsfs_ctx* c, KeyParams& p) {
   p.ns1 = c->ns1; p.ns2 = c->ns2; p.W1 = c->W1; p.W2 = c->W2;
   p.S = c->S;
   p.G = c->dG; p.cnt = c->dCnt; p.pos = c->dPos; p.flags = c->dFlags; p.fix = c->dFix; p.nfix = c->nfix;
-  p.rec = c->d_rec; p.hist = c->d_hist; p.gstride = c->gstride;
+  p.rec = c->d_rec; p.fmt = c->fmt; p.hist = c->d_hist; p.gstride = c->gstride;
   p.chrom_off = c->d_off; p.C = c->C; p.err = c->d_err;
   p.cr = std::min(c->R1, CORNER); p.cc = std::min(c->R2, CORNER);
   p.h1a = std::min(c->R1, H1CAP); p.h1b = std::min(c->R2, H1CAP);
@@ -494,10 +495,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   CKR(peer_settle(c));  // peers may still be pushing the previous exchange into the histogram
-  if (c->pipe_armed) {  // window sums of an earlier pass that no scan consumed: let them finish before the records change
-    CK(cudaStreamWaitEvent(st, c->ev_scored, 0));
-    c->pipe_armed = false;
-  }
+  c->ws_ready = false;  // the records (and any window sums) are rewritten by this pass
   CK(cudaEventRecord(c->ev[EV_BG0], st));
   const int NG = mode == TDSFS_BG_PER_CHROM ? c->C : 1;
   c->gstride = (long long)c->bins2d + c->R1 + c->R2;
@@ -518,6 +516,16 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   c->results_ready = false;
   c->per_chrom_scoring = mode == TDSFS_BG_PER_CHROM;
 
+  // record format: 4-byte narrow records when the 2D cell plus two missing-diploid counts fit 32 bits (genotype entry,
+  // no half-call fix-ups, no more sample columns than the declared panel); 8-byte wide records otherwise
+  c->fmt = RecFmt{0, 0, 0, 0};
+  if (c->dG && !c->force_wide && c->nfix == 0 && c->ns1 <= c->n1 && c->ns2 <= c->n2 && !getenv("TDSFS_REC_WIDE")) {
+    int b1 = 1, b2 = 1;
+    while ((1 << b1) <= 2 * c->n1) ++b1;
+    while ((1 << b2) <= 2 * c->n2) ++b2;
+    const int md = (32 - b1 - b2) / 2;
+    if (md >= 3) c->fmt = RecFmt{1, b1, b2, md};
+  }
   KeyParams p;
   fill_key_params(c, p);
   p.bg_lo = bg_lo; p.bg_hi = bg_hi;
@@ -576,70 +584,91 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       p.tile_blocks = blk_bytes <= 8192 ? std::max(2, 8192 / blk_bytes) : 1;  // one TMA bulk copy per tile
       if (const char* e = getenv("TDSFS_K1_TILE")) p.tile_blocks = std::max(1, atoi(e));  // tuning knob: blocks per tile
       p.stage_bytes = p.tile_blocks * blk_bytes;
-      const int fit = (226 * 1024 - hist_bytes) / (p.stage_bytes + 8);
+      const bool old_kernel = getenv("TDSFS_K1_OLD") != nullptr || getenv("TDSFS_K1_PROBE") != nullptr;  // A/B + bandwidth probe
+      // ---- fused scan: a plan for (W, mode) is pending -> the count kernel also leaves every window's background-independent sums
+      FusedParams q;
+      memset(&q, 0, sizeof q);
+      const int hist_words = (p.cr * p.cc + p.h1a + p.h1b + 3) & ~3;
+      q.nw1 = (c->n1 + 2) / 2; q.nw2 = (c->n2 + 2) / 2;
+      const int tab_words = HASH_SLOTS + ((q.nw1 + q.nw2 + 3) & ~3);
+      const int stage_stride = p.stage_bytes + p.tile_blocks * BLK * 4;
+      const int smem_max = 227 * 1024;
+      bool fuse = !old_kernel && c->plan_W > 0 && c->plan_W <= 0x7FFFFFFFLL && score_small_ok(c->n1, c->n2, c->bins2d) &&
+                  !(c->plan_snp && c->plan_W > WCAP) && !getenv("TDSFS_NO_FUSE");
+      int fit = (smem_max - hist_words * 4 - 16) / (stage_stride + 8 + (fuse ? tab_words * 4 : 0));
+      if (fuse && fit < 4) {  // panel too large for warp-private window tables beside the ring: plain count kernel + the table scorer
+        fuse = false;
+        fit = (smem_max - hist_words * 4 - 16) / (stage_stride + 8);
+      }
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
       p.cwarps = std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
       if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
-      int depth = 1;  // stages per warp
-      if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, std::min(fit / p.cwarps, atoi(e)));  // tuning knob
-      p.nstage = p.cwarps * depth;
-      const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
-      void (*kern)(KeyParams) = k1_genotypes<0, 0>;
-      if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
-      else if (c->W1 == 14 && c->W2 == 14) kern = k1_genotypes<14, 14>;   // 200 + 200 diploids (BASELINE config 4)
-      if (getenv("TDSFS_K1_PROBE")) kern = k1_probe_ring;  // bandwidth probe, no spectra (profiling only)
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      p.interleave = (p.bg_group == nullptr) ? 1 : 0;
-      if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
-      // experimental: K1 in row chunks with the window-only scorer of each chunk on a second stream (tdsfs_pipeline.cuh)
-      const int gwords = score_group_smem_words(c->n1, c->n2);
-      const long long tile_rows = (long long)p.tile_blocks * BLK;
-      int nch = (int)std::min<long long>(PIPE_MAX_CHUNKS, c->S / (4LL << 20));
-      if (const char* e = getenv("TDSFS_PIPELINE_CHUNKS")) nch = std::max(1, std::min(PIPE_MAX_CHUNKS, atoi(e)));
-      const bool pipe = c->pipe && mode == TDSFS_BG_GENOME && p.bg_lo < 0 && c->plan_W > 0 && !c->plan_snp && !c->dFlags &&
-                        c->chunks.size() == 1 && !c->chunks[0].ev && nch >= 2 && kern != k1_probe_ring &&
-                        score_small_ok(c->n1, c->n2, c->bins2d) && SCORE_WARPS * gwords * 4 <= 200 * 1024 && c->S < 0x7FFFFFFFLL;
-      if (pipe) {
-        const long long ncand = c->cand_off_host[c->C];
-        PipeParams q;
-        memset(&q, 0, sizeof q);
-        q.s.rec = c->d_rec; q.s.wlo = c->d_wlo; q.s.whi = c->d_whi; q.s.ncand = ncand;
-        q.s.n1 = c->n1; q.s.n2 = c->n2; q.s.bins2d = c->bins2d; q.s.lnI = c->d_lnI;
-        q.s.r_count = c->r_count; q.s.r_n2 = c->r_n2; q.s.r_n1a = c->r_n1a; q.s.r_n1b = c->r_n1b;
-        q.s.r_T2 = c->r_T2; q.s.r_T1a = c->r_T1a; q.s.r_T1b = c->r_T1b; q.s.r_flags = c->r_flags;
-        q.dxI = c->d_dxI;
-        const int smem3 = SCORE_WARPS * gwords * 4;
-        CK(cudaFuncSetAttribute(k3a_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        CK(cudaMemsetAsync(c->d_pipe_work, 0, sizeof(unsigned long long) * PIPE_MAX_CHUNKS, st));
-        CK(cudaStreamWaitEvent(c->score_stream, c->ev_plan, 0));  // window boundaries (K2 on the plan stream)
-        const long long rows_per = ((c->S + nch - 1) / nch + tile_rows - 1) / tile_rows * tile_rows;
-        int i = 0;
-        for (long long r0 = 0; r0 < c->S; r0 += rows_per, ++i) {
-          p.r0 = r0; p.r1 = std::min<long long>(c->S, r0 + rows_per);
-          const long long ntiles = ((p.r1 - p.r0 + BLK - 1) / BLK + p.tile_blocks - 1) / p.tile_blocks;
-          kern<<<(int)std::min<long long>(ntiles, (long long)c->sm_count), p.cwarps * 32, smem, st>>>(p);
-          CK(cudaEventRecord(c->ev_chunk[i], st));
-          CK(cudaStreamWaitEvent(c->score_stream, c->ev_chunk[i], 0));
-          q.row_lo = (int)p.r0; q.row_hi = (int)p.r1; q.work = c->d_pipe_work + i;
-          // one CTA per SM while a count kernel follows (its CTA + one of these fill an SM's shared memory; more would
-          // keep the next chunk's count CTAs from being placed), every slot for the last chunk
-          const bool last_chunk = p.r1 >= c->S;
-          k3a_window_sums<<<c->sm_count * (last_chunk ? 4 : 1), SCORE_WARPS * 32, smem3, c->score_stream>>>(q);
-          c->launches += 2;
+      p.nstage = p.cwarps;
+      if (old_kernel) {
+        int depth = 1;  // stages per warp
+        if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, std::min(fit / p.cwarps, atoi(e)));  // tuning knob
+        p.nstage = p.cwarps * depth;
+        const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
+        void (*kern)(KeyParams) = k1_genotypes<0, 0>;
+        if (c->W1 == 32 && c->W2 == 32) kern = k1_genotypes<32, 32>;
+        else if (c->W1 == 14 && c->W2 == 14) kern = k1_genotypes<14, 14>;
+        if (getenv("TDSFS_K1_PROBE")) kern = k1_probe_ring;  // bandwidth probe, no spectra (profiling only)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        p.interleave = (p.bg_group == nullptr) ? 1 : 0;
+        if (const char* e = getenv("TDSFS_K1_INTERLEAVE")) p.interleave = atoi(e) != 0 && p.bg_group == nullptr;
+        for (auto& ch : c->chunks) {
+          if (ch.r1 <= ch.r0) continue;
+          if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
+          p.r0 = ch.r0; p.r1 = ch.r1;
+          const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
+          const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
+          const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
+          kern<<<grid, p.cwarps * 32, smem, st>>>(p);
+          c->launches++;
         }
-        CK(cudaEventRecord(c->ev_scored, c->score_stream));
-        c->pipe_armed = true;
-        c->pipe_W = c->plan_W;
-      } else
-      for (auto& ch : c->chunks) {
-        if (ch.r1 <= ch.r0) continue;
-        if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
-        p.r0 = ch.r0; p.r1 = ch.r1;
-        const long long nblk = (ch.r1 - ch.r0 + BLK - 1) / BLK;
-        const long long ntiles = (nblk + p.tile_blocks - 1) / p.tile_blocks;
-        const int grid = (int)std::min<long long>(ntiles, (long long)c->sm_count);
-        kern<<<grid, p.cwarps * 32, smem, st>>>(p);
-        c->launches++;
+      } else {
+        q.wmode = fuse ? (c->plan_snp ? 2 : 1) : 0;
+        q.tab_words = fuse ? tab_words : 0;
+        if (fuse) {
+          const long long ncand = c->cand_off_host[c->C];
+          if (ncand > c->ws_cap) {
+            CK(cudaStreamSynchronize(st));
+            dev_free(c->d_ws);
+            CKR(dev_alloc(&c->d_ws, ncand * 4));
+            c->ws_cap = ncand;
+          }
+          q.W = (uint32_t)c->plan_W;
+          q.Wmagic = (uint32_t)std::min<unsigned long long>(0xFFFFFFFFull, (1ull << 32) / (unsigned long long)c->plan_W);
+          q.cand_off = c->d_cand_off;
+          q.ncand = ncand;
+          q.ws = c->d_ws;
+          q.dxI = c->d_dxI;
+          q.lnI = c->d_lnI;
+        } else {
+          q.nw1 = q.nw2 = 0;
+        }
+        q.pos_tma = (((uintptr_t)c->dPos) & 15) == 0 && !getenv("TDSFS_NO_POS_TMA");
+        const int smem = p.cwarps * (stage_stride + q.tab_words * 4) + ((p.cwarps + 1) & ~1) * 8 + hist_words * 4;
+        void (*kern)(FusedParams) = k1_fused<0, 0>;
+        if (c->W1 == 32 && c->W2 == 32) kern = k1_fused<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
+        else if (c->W1 == 14 && c->W2 == 14) kern = k1_fused<14, 14>;   // 200 + 200 diploids (BASELINE config 4)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const long long tile_rows = (long long)p.tile_blocks * BLK;
+        for (auto& ch : c->chunks) {
+          if (ch.r1 <= ch.r0) continue;
+          if (ch.ev) CK(cudaStreamWaitEvent(st, ch.ev, 0));
+          p.r0 = ch.r0; p.r1 = ch.r1;
+          const long long ntiles = (ch.r1 - ch.r0 + tile_rows - 1) / tile_rows;
+          const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + p.cwarps - 1) / p.cwarps, (long long)c->sm_count));
+          q.k = p;
+          kern<<<grid, p.cwarps * 32, smem, st>>>(q);
+          c->launches++;
+        }
+        if (fuse) {
+          c->fused_W = c->plan_W;
+          c->fused_snp = c->plan_snp;
+          c->ws_ready = true;
+        }
       }
     }
   } else {
@@ -661,7 +690,12 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
     CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
     if (err & 1) {
       c->keys_ready = false;
+      c->ws_ready = false;
       return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
+    }
+    if ((err & 8) && !c->force_wide) {  // a SNP's missing-call counts do not fit the narrow record: redo with wide records
+      c->force_wide = true;
+      return tdsfs_background(c, mode, bg_chrom, bg_lo, bg_hi);
     }
   }
   return 0;
@@ -947,13 +981,15 @@ extern "C" int tdsfs_fetch_results(tdsfs_t* c, tdsfs_result_t* out, int64_t cap,
   D2H(T1D_p2, r_T1b, double);
   D2H(flags, r_flags, uint8_t);
 #undef D2H
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (n_windows) *n_windows = c->ncand;
-  return 0;
+  return deferred_error(c, err);
 }
 
 // candidate list of (W, mode) on the device + K2 launch on stream `st`
-static int launch_bounds(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t st) {
+static int ensure_candidates(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t st) {
   if (c->cand_W != W || c->cand_snp != (int)snp_mode) {  // candidate offsets cached per (size, mode): no sync in steady state
     CKR(candidates(c, W, snp_mode, c->cand_off_host));
     CKR(ensure_windows(c, c->cand_off_host[c->C]));
@@ -962,7 +998,13 @@ static int launch_bounds(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t 
     CK(cudaMemcpyAsync(c->d_cand_off, c->cand_off_host.data(), (size_t)(c->C + 1) * 8, cudaMemcpyHostToDevice, st));
     c->cand_W = W;
     c->cand_snp = snp_mode;
+    c->ws_ready = false;
   }
+  return 0;
+}
+
+static int launch_bounds(tdsfs_ctx* c, long long W, bool snp_mode, cudaStream_t st) {
+  CKR(ensure_candidates(c, W, snp_mode, st));
   const long long ncand = c->cand_off_host[c->C];
   if (ncand > 0) {
     CK(cudaMemsetAsync(c->d_nlarge, 0, sizeof(int), st));
@@ -986,6 +1028,7 @@ static int plan(tdsfs_ctx* c, long long W, bool snp_mode) {
   if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
   if (!c->dPos) return fail(TDSFS_ERR_STATE, "load data first");
   CK(cudaSetDevice(c->device));
+  CKR(ensure_candidates(c, W, snp_mode, c->stream));     // the fused count kernel (main stream) reads the candidate offsets too
   CK(cudaEventRecord(c->ev_fork, c->stream));            // after everything queued so far (previous scan reads the old plan)
   CK(cudaStreamWaitEvent(c->plan_stream, c->ev_fork, 0));
   CK(cudaEventRecord(c->ev_plan0, c->plan_stream));
@@ -1024,24 +1067,41 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     s.lb2 = c->d_lb2; s.lb1a = c->d_lb1a; s.lb1b = c->d_lb1b; s.B = c->d_B; s.lnI = c->d_lnI;
     s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
-    // small windows: one warp each
+    s.fmt = c->fmt; s.C2 = c->R2;
+    const long long sstride = (long long)c->bins2d + c->n1 + 1 + c->n2 + 1;
+    if (!c->d_scratch) {  // dense scratch of the large-window path, one slab per CTA
+      c->large_ctas = (int)std::max<long long>(8, std::min<long long>(2 * c->sm_count, (256LL << 20) / (sstride * 4)));
+      CKR(dev_alloc(&c->d_scratch, sstride * c->large_ctas));
+      CK(cudaMemsetAsync(c->d_scratch, 0, (size_t)(sstride * c->large_ctas) * 4, st));
+    }
+    s.scratch = c->d_scratch;
+    const int gwords = score_group_smem_words(c->n1, c->n2);
+    if (c->ws_ready && c->fused_W == W && c->fused_snp == (int)snp_mode) {
+      // fused scan: the count kernel left every small window's background-independent sums; one launch gathers ln b over
+      // the records, finishes the statistics and scores the large windows
+      FinishParams f;
+      memset(&f, 0, sizeof f);
+      f.s = s;
+      f.ws = c->d_ws;
+      f.cr = c->fmt.narrow ? std::min(CORNER, std::min(c->R1, c->R2)) : 0;
+      const size_t tab_bytes = ((size_t)f.cr * f.cr + c->n1 + 1 + c->n2 + 1) * sizeof(double);
+      f.use_smem = !c->per_chrom_scoring && tab_bytes <= 96 * 1024;
+      if (!f.use_smem) f.cr = 0;
+      f.large_ctas = c->large_ctas;
+      const int smem = f.use_smem ? (int)tab_bytes : 0;
+      CK(cudaFuncSetAttribute(k3_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * 4));
+      k3_finish<<<grid, 256, smem, st>>>(f);
+      c->launches++;
+      c->last_fused = true;
+      CK(cudaEventRecord(c->ev[EV_K3S], st));
+      CK(cudaEventRecord(c->ev[EV_K3L], st));
+      CK(cudaGetLastError());
+    } else {
+    c->last_fused = false;
     // small windows: groups of G warps per window over shared-memory tables (skipped for panels beyond their limits:
     // K2 then lists every window as "large")
-    const int gwords = score_group_smem_words(c->n1, c->n2);
-    const bool armed = c->pipe_armed;
-    if (armed) {  // window sums computed under K1 (tdsfs_pipeline.cuh): wait for them whether or not this scan uses them
-      CK(cudaStreamWaitEvent(st, c->ev_scored, 0));
-      c->pipe_armed = false;
-    }
-    if (armed && planned && !snp_mode && c->pipe_W == W && !c->dFlags && !c->per_chrom_scoring && !c->float_bg) {
-      PipeParams q;
-      memset(&q, 0, sizeof q);
-      q.s = s;
-      q.dxI = c->d_dxI;
-      const int grid = (int)std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * 8);
-      k3b_gather_finish<<<grid, 256, 0, st>>>(q, c->d_large, c->d_nlarge);
-      c->launches++;
-    } else if (score_small_ok(c->n1, c->n2, c->bins2d) && gwords * 4 <= 200 * 1024) {
+    if (score_small_ok(c->n1, c->n2, c->bins2d) && gwords * 4 <= 200 * 1024) {
       // one warp per window when every resident warp gets many windows; two warps per window for small scans
       // (a rank of an 8-GPU run: ~4 windows per warp -> finer granularity evens out the tail; measured 0.135 -> 0.122 ms)
       int G = c->score_group_warps;
@@ -1071,18 +1131,12 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       c->launches++;
     }
     CK(cudaEventRecord(c->ev[EV_K3S], st));
-    // large windows: one CTA each over dense global scratch
-    const long long sstride = (long long)c->bins2d + c->n1 + 1 + c->n2 + 1;
-    if (!c->d_scratch) {
-      c->large_ctas = (int)std::max<long long>(8, std::min<long long>(2 * c->sm_count, (256LL << 20) / (sstride * 4)));
-      CKR(dev_alloc(&c->d_scratch, sstride * c->large_ctas));
-      CK(cudaMemsetAsync(c->d_scratch, 0, (size_t)(sstride * c->large_ctas) * 4, st));
-    }
-    s.scratch = c->d_scratch;
+    // large windows: one CTA each over dense scratch
     k3_score_large<<<c->large_ctas, LARGE_THREADS, 0, st>>>(s);
     c->launches++;
     CK(cudaEventRecord(c->ev[EV_K3L], st));
     CK(cudaGetLastError());
+    }
   } else {
     CK(cudaEventRecord(c->ev[EV_K3S], st));
     CK(cudaEventRecord(c->ev[EV_K3L], st));
@@ -1107,9 +1161,7 @@ extern "C" int tdsfs_check(tdsfs_t* c) {
   CK(cudaStreamSynchronize(c->stream));
   int err = 0;
   CK(cudaMemcpy(&err, c->d_err, sizeof err, cudaMemcpyDeviceToHost));
-  if (err & 4) return fail(TDSFS_ERR_CUDA, "peer exchange: a rank did not reach the barrier in time");
-  if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
-  return 0;
+  return deferred_error(c, err);
 }
 
 extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) {
@@ -1120,10 +1172,16 @@ extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result
   if (!r) r = tdsfs_background(c, bg_mode, 0, -1, -1);
   if (!r) r = tdsfs_finalize_background(c);
   if (!r) r = scan(c, W, false, out, cap, n);
+  if (!r && (was_sync || out)) r = tdsfs_check(c);  // fully asynchronous otherwise: the caller synchronises and calls tdsfs_check
+  if (r == TDSFS_ERR_RETRY) {  // a SNP did not fit the 4-byte record: the handle switched to 8-byte records, run the pass again
+    r = plan(c, W, false);
+    if (!r) r = tdsfs_background(c, bg_mode, 0, -1, -1);
+    if (!r) r = tdsfs_finalize_background(c);
+    if (!r) r = scan(c, W, false, out, cap, n);
+    if (!r) r = tdsfs_check(c);
+  }
   c->sync = was_sync;
-  if (r) return r;
-  if (!was_sync && !out) return 0;  // fully asynchronous: the caller synchronises and may call tdsfs_check
-  return tdsfs_check(c);
+  return r;
 }
 
 extern "C" int tdsfs_window_spectra(tdsfs_t* c, int64_t window, uint64_t* s2, uint64_t* s1a, uint64_t* s1b) {
@@ -1241,3 +1299,10 @@ extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
 }
 
 extern "C" int64_t tdsfs_launch_count(tdsfs_t* c) { return c ? c->launches : 0; }
+
+extern "C" int tdsfs_scan_info(tdsfs_t* c, int32_t* fused, int32_t* record_bytes) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  if (fused) *fused = c->last_fused ? 1 : 0;
+  if (record_bytes) *record_bytes = c->fmt.narrow ? 4 : 8;
+  return 0;
+}

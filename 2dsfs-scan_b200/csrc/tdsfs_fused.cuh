@@ -1,0 +1,540 @@
+// tdsfs_fused.cuh -- the fused scan of the genotype-level entry:
+//
+//   k1_fused    ONE pass over the 2-bit genotype matrix does everything that does not need the final background:
+//               per-SNP counts -> joint fold -> record store -> background histograms (as the plain count kernel), AND the
+//               background-independent half of every window's statistics.  With
+//                   T = 2 ( sum_bins x ln x  -  sum_SNPs ln b[bin_s]  -  N (ln N - ln B) )
+//               (algebraically the reference's 2 (logpmf(x; x/N) - logpmf(x; b/B)), twoDSFS_class.py:625-684, :478-537)
+//               the first sum and N depend on the window alone.  Every warp owns a CONTIGUOUS range of SNPs whose ends are
+//               snapped to window starts, streams it through its own TMA stage (genotype tile + the tile's positions), finds
+//               the window of each SNP from its position ((pos-1)//W, :898) or its rank in the chromosome (:1515-1535), and
+//               keeps the current window's spectra in warp-private shared-memory tables: an open-addressing table of 2D bins
+//               whose insert returns the bin's old count c (the sum grows by dx[c] = (c+1) ln(c+1) - c ln c) and packed
+//               16-bit folded 1D bins walked when the window closes.  Per window it leaves {sum2D, sum1D_p1, sum1D_p2, N's}.
+//   k3_finish   after the background is final (all-reduce + ln tables): per window, the gather sum_SNPs ln b[bin_s] over the
+//               window's records and the three statistics.  The spectra for which the reference returns exactly 0.0 (a window
+//               that is its own background, a window with one populated bin) are re-scored per bin.  Windows larger than the
+//               warp tables (> WCAP SNPs) are scored by the CTA path over dense scratch in the same launch.
+#pragma once
+#include "tdsfs_kernels.cuh"
+
+namespace tdsfs {
+
+// meta word of a window's sums: count_snps in bits 0..9, then the flags
+constexpr uint32_t WS_ONE_2D = 1u << 10, WS_ONE_1A = 1u << 11, WS_ONE_1B = 1u << 12, WS_NALL = 1u << 13;
+
+struct FusedParams {
+  KeyParams k;
+  int wmode;                  // 0 = no window sums (plain count kernel), 1 = fixed-bp windows, 2 = fixed-SNP windows
+  uint32_t W, Wmagic;         // window size (bp or SNPs) and min(floor(2^32 / W), 2^32 - 1)
+  const long long* cand_off;  // [C+1] first candidate window of every chromosome
+  long long ncand;
+  double* ws;                 // [ncand][4] = sum2D, sum1D_p1, sum1D_p2, bits(N2 | N1a << 10 | N1b << 20, meta)
+  const double* dxI;          // dx[m] = (m+1) ln(m+1) - m ln m, m < LN_TABLE
+  const double* lnI;          // ln m
+  int pos_tma;                // the tile's positions ride the TMA ring (16-byte aligned position array)
+  int tab_words;              // per-warp window tables: HASH_SLOTS + packed 1D words, a multiple of 4
+  int nw1, nw2;               // packed 1D words per population: (n + 2) / 2
+};
+
+// dx[m] = (m+1) ln(m+1) - m ln m, written as ln(m+1) + m log1p(1/m) so that no large terms cancel
+__global__ void k_dx_table(double* t, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = i ? log((double)i + 1.0) + (double)i * log1p(1.0 / (double)i) : 0.0;
+}
+
+// exact x / W for x < 2^32 with M = min(floor(2^32 / W), 2^32 - 1): the estimate is at most one short
+__device__ __forceinline__ uint32_t udiv_magic(uint32_t x, uint32_t W, uint32_t M) {
+  uint32_t qd = __umulhi(x, M);
+  if (x - qd * W >= W) ++qd;
+  return qd;
+}
+
+struct ChromWin {
+  int c = -1, lo = 0, hi = -1;  // chromosome and its row range
+  int cbase = 0;                // first candidate window of the chromosome
+  int nfull = 0;                // fixed-SNP mode: number of full windows
+};
+
+__device__ __forceinline__ void chrom_win(const FusedParams& q, int s, ChromWin& cw) {
+  if (s >= cw.lo && s < cw.hi) return;
+  const KeyParams& p = q.k;
+  int lo = 0, hi = p.C;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(p.chrom_off + mid) <= s) lo = mid; else hi = mid;
+  }
+  cw.c = lo;
+  cw.lo = (int)__ldg(p.chrom_off + lo);
+  cw.hi = (int)__ldg(p.chrom_off + lo + 1);
+  cw.cbase = (int)__ldg(q.cand_off + lo);
+  cw.nfull = q.wmode == 2 ? (int)((uint32_t)(cw.hi - cw.lo) / q.W) : 0;
+}
+
+// candidate-window id of SNP s at position pv; -1 = in no window (tail of a chromosome in fixed-SNP mode)
+__device__ __forceinline__ int window_id(const FusedParams& q, int s, int pv, ChromWin& cw) {
+  chrom_win(q, s, cw);
+  int id;
+  if (q.wmode == 1) {
+    id = cw.cbase + (int)udiv_magic(pv > 0 ? (uint32_t)(pv - 1) : 0u, q.W, q.Wmagic);  // pos 0 falls in window 0 (Q10)
+  } else {
+    const int j = (int)udiv_magic((uint32_t)(s - cw.lo), q.W, q.Wmagic);
+    id = j < cw.nfull ? cw.cbase + j : -1;
+  }
+  return (long long)id < q.ncand ? id : -1;  // unsorted positions must not write out of bounds
+}
+
+// Snap a range boundary `t` (a tile-aligned row) back to the first SNP of the window that contains it, so that no window
+// of at most WCAP SNPs is split between two warps (warp-cooperative: all lanes call, all return the same value).
+// is_start = the returned row starts a window (or lies in none); false when the window began more than WCAP rows earlier
+// (such a window is larger than the warp tables: nobody sums it here, the CTA path scores it).
+__device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_start, int lane) {
+  const KeyParams& p = q.k;
+  is_start = true;
+  if (t <= 0) return 0;
+  if (t >= (int)p.S) return (int)p.S;
+  if (q.wmode == 0) return t;
+  ChromWin cw;
+  chrom_win(q, t, cw);
+  if (t == cw.lo) return t;
+  if (q.wmode == 2) {
+    const int j = (int)udiv_magic((uint32_t)(t - cw.lo), q.W, q.Wmagic);
+    if (j >= cw.nfull) return t;  // tail of the chromosome: no window
+    if (q.W > (uint32_t)WCAP) {
+      is_start = (t - cw.lo) == j * (int)q.W;
+      return t;
+    }
+    return cw.lo + j * (int)q.W;
+  }
+  const int k = window_id(q, t, __ldg(p.pos + t), cw);
+  const int lo = max(cw.lo, t - WCAP);
+  const int span = t - lo;               // 1 .. WCAP
+  const int step = (span + 31) >> 5;     // 1 .. 24
+  // round 1: lanes probe lo + lane * step (window ids are monotone in the row: false ... false true ... true, t is true)
+  const int s1 = lo + lane * step;
+  const bool in1 = s1 < t ? window_id(q, s1, __ldg(p.pos + s1), cw) == k : true;
+  const uint32_t b1 = __ballot_sync(0xffffffffu, in1);
+  const int f = __ffs(b1) - 1;           // b1 != 0: the lanes with s1 >= t vote true (31 * step may be < span: then f may be 32 - handled below)
+  if (b1 == 0u || f < 0) {               // every probe lies before the window: it starts in (lo + 31 step, t]
+    const int base = lo + 31 * step + 1;
+    const int sc = base + lane;
+    const bool in2 = sc < t ? window_id(q, sc, __ldg(p.pos + sc), cw) == k : true;
+    const uint32_t b2 = __ballot_sync(0xffffffffu, in2);
+    return min(base + __ffs(b2) - 1, t);
+  }
+  if (f == 0) {                          // row lo already belongs to the window
+    if (lo == cw.lo) return lo;          // ... because the chromosome starts there
+    is_start = false;                    // ... or the window began earlier: larger than WCAP rows
+    return t;
+  }
+  // round 2: the start lies in (lo + (f-1) step, lo + f step]
+  const int base = lo + (f - 1) * step + 1;
+  const int sc = base + lane;
+  const int top = min(lo + f * step, t);
+  const bool in2 = sc < top ? window_id(q, sc, __ldg(p.pos + sc), cw) == k : true;
+  const uint32_t b2 = __ballot_sync(0xffffffffu, in2);
+  return min(base + __ffs(b2) - 1, top);
+}
+
+template <int TW1, int TW2>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant__ FusedParams q) {
+  const KeyParams& p = q.k;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W1 = TW1 > 0 ? TW1 : p.W1, W2 = TW2 > 0 ? TW2 : p.W2;
+  const int RW = W1 + W2;
+  const int tile_rows = p.tile_blocks * BLK;
+  const int stage_stride = p.stage_bytes + tile_rows * 4;  // genotype tile, then the tile's positions
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.cwarps * stage_stride);
+  SinkSmem sm;
+  sm.corner = reinterpret_cast<uint32_t*>(full + ((p.cwarps + 1) & ~1));
+  sm.h1a = sm.corner + p.cr * p.cc;
+  sm.h1b = sm.h1a + p.h1a;
+  const int nhist = p.cr * p.cc + p.h1a + p.h1b;
+  uint32_t* tab = sm.corner + ((nhist + 3) & ~3) + (size_t)warp * q.tab_words;  // hash table | 1D pop1 | 1D pop2
+  uint32_t* w1a = tab + HASH_SLOTS;
+  uint32_t* w1b = w1a + q.nw1;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.cwarps; ++i) mbar_init(full + i, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < nhist; i += blockDim.x) sm.corner[i] = 0;
+  if (q.wmode && warp < p.cwarps) {
+    for (int i = lane; i < HASH_SLOTS; i += 32) tab[i] = EMPTY_KEY;
+    for (int i = lane; i < q.nw1 + q.nw2; i += 32) w1a[i] = 0;
+  }
+  __syncthreads();
+
+  // part jj of the launch's rows [r0, r1) starts at a tile-aligned row near r0 + (r1 - r0) jj / nparts
+  const int r0 = (int)p.r0, r1 = (int)p.r1, S = (int)p.S;
+  const int nparts = gridDim.x * p.cwarps;
+  auto target = [&](int jj) -> int {
+    if (jj <= 0) return r0;
+    if (jj >= nparts) return r1;
+    const long long t = r0 + (long long)(r1 - r0) * jj / nparts;
+    return max(r0, (int)(t / tile_rows * tile_rows));
+  };
+  ChromCache cc;
+  const int cta_group = tile_group(p, target(blockIdx.x * p.cwarps), cc);
+
+  if (warp < p.cwarps) {
+    const int j = blockIdx.x * p.cwarps + warp;
+    bool st0, st1;
+    const int slo = snap_row(q, target(j), st0, lane);
+    const int shi = snap_row(q, target(j + 1), st1, lane);
+    if (slo < shi) {
+      uint8_t* stage = smem + (size_t)warp * stage_stride;
+      const int* spos = reinterpret_cast<const int*>(stage + p.stage_bytes);
+      uint64_t* bar = full + warp;
+      const long long block_words = (long long)RW * BLK;
+      const int b_end = (r1 + BLK - 1) / BLK;  // blocks this launch may read (later ones may still be uploading)
+      const int S4 = S & ~3;                   // positions below S4 come through TMA in whole 16-byte groups
+      const int t_begin = slo / tile_rows, t_end = (shi - 1) / tile_rows + 1;
+      auto issue = [&](int t) {  // lane 0 only
+        const int blk0 = t * p.tile_blocks;
+        const int nb = min(p.tile_blocks, b_end - blk0);
+        const uint32_t gbytes = (uint32_t)(nb * block_words * 4);
+        uint32_t pbytes = 0;
+        if (q.pos_tma) pbytes = (uint32_t)max(0, min(nb * BLK, S4 - blk0 * BLK)) * 4u;
+        mbar_arrive_expect_tx(bar, gbytes + pbytes);
+        bulk_g2s_stream(stage, p.G + (long long)blk0 * block_words, gbytes, bar);
+        if (pbytes) bulk_g2s(stage + p.stage_bytes, p.pos + (long long)blk0 * BLK, pbytes, bar);
+      };
+      if (lane == 0) issue(t_begin);
+      uint32_t ph = 0;
+
+      // ---- state of the window the warp is in
+      int cur_id = -2;                 // -2 = none yet, -1 = rows outside every window
+      bool overflow = false;           // the window is not summed here (more than WCAP SNPs, or entered mid-way)
+      bool pending_skip = !st0;
+      int wcount = 0;
+      double w2 = 0.0;
+      uint32_t nn = 0, m2 = 0, cflag = 0, nall = 0;
+      ChromWin cw;
+      const uint32_t last = (uint32_t)p.bins2d - 1;
+      constexpr uint32_t F10 = (1u << KEY_SHIFT) - 1;
+
+      auto close_window = [&]() {
+        __syncwarp();
+        if (cur_id >= 0) {
+          if (!overflow) {
+            double a1 = 0.0, b1 = 0.0;
+            uint32_t ma = 0, mb = 0;
+            for (int i = lane; i < q.nw1; i += 32) {
+              const uint32_t v = w1a[i];
+              if (v) {
+                w1a[i] = 0;
+                const uint32_t x0 = v & 0xFFFF, x1 = v >> 16;
+                if (x0 > 1) a1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), a1);
+                if (x1 > 1) a1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), a1);
+                ma = max(ma, max(x0, x1));
+              }
+            }
+            for (int i = lane; i < q.nw2; i += 32) {
+              const uint32_t v = w1b[i];
+              if (v) {
+                w1b[i] = 0;
+                const uint32_t x0 = v & 0xFFFF, x1 = v >> 16;
+                if (x0 > 1) b1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), b1);
+                if (x1 > 1) b1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), b1);
+                mb = max(mb, max(x0, x1));
+              }
+            }
+            const uint32_t nt = __reduce_add_sync(0xffffffffu, nn);
+            const uint32_t m2t = __reduce_max_sync(0xffffffffu, m2);
+            ma = __reduce_max_sync(0xffffffffu, ma);
+            mb = __reduce_max_sync(0xffffffffu, mb);
+            const uint32_t cft = __reduce_add_sync(0xffffffffu, cflag);
+            const uint32_t nat = __reduce_add_sync(0xffffffffu, nall);
+            const double w2t = warp_sum(w2);
+            a1 = warp_sum(a1);
+            b1 = warp_sum(b1);
+            const uint32_t N2 = nt & F10, N1a = (nt >> 10) & F10, N1b = nt >> 20;
+            const uint32_t meta = cft | (N2 && m2t + 1 == N2 ? WS_ONE_2D : 0u) | (N1a && ma == N1a ? WS_ONE_1A : 0u) |
+                                  (N1b && mb == N1b ? WS_ONE_1B : 0u) | (nat ? WS_NALL : 0u);
+            if (lane < 4) {
+              const double v = lane == 0 ? w2t : (lane == 1 ? a1 : (lane == 2 ? b1 : __hiloint2double((int)meta, (int)nt)));
+              q.ws[(long long)cur_id * 4 + lane] = v;
+            }
+          } else {
+            for (int i = lane; i < q.nw1 + q.nw2; i += 32) w1a[i] = 0;
+          }
+          uint4* t4 = reinterpret_cast<uint4*>(tab);
+#pragma unroll
+          for (int i = 0; i < HASH_SLOTS / 128; ++i) t4[lane + i * 32] = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
+        }
+        w2 = 0.0;
+        nn = m2 = cflag = nall = 0;
+        wcount = 0;
+        __syncwarp();
+      };
+
+      for (int t = t_begin; t < t_end; ++t) {
+        const int blk0 = t * p.tile_blocks;
+        const int nb = min(p.tile_blocks, b_end - blk0);
+        mbar_wait(bar, ph);
+        ph ^= 1;
+        const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+        for (int b = 0; b < nb; ++b) {
+          const int sb = (blk0 + b) * BLK;
+          const int s = sb + lane;
+          const bool live = sb + BLK > slo && sb < shi;  // warp-uniform: the block holds rows of this warp's range
+          const bool act = s >= slo && s < shi;
+          uint32_t T1 = 0, M1 = 0, T2 = 0, M2 = 0;
+          int pv = 0;
+          if (live) {
+            const uint32_t* rowp = tile + (size_t)b * block_words + lane;
+            if (TW1 > 0 && TW1 == TW2) {
+              count_two_blocks_b32<TW1>(rowp, rowp + W1 * BLK, T1, M1, T2, M2);
+            } else {
+              count_block_b32<TW1>(rowp, W1, T1, M1);
+              count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
+            }
+            if (q.wmode == 1 || p.bg_lo >= 0) {
+              if (q.pos_tma && s < S4) pv = spos[b * BLK + lane];
+              else if (s < S) pv = __ldg(p.pos + s);
+            }
+          }
+          if (b == nb - 1) {
+            // the stage has been read completely: refill it BEFORE the fold / record / histogram / window work of its
+            // last block, so that work overlaps the next load instead of delaying it
+            __syncwarp();
+            if (lane == 0 && t + 1 < t_end) {
+              fence_proxy_async();  // order this warp's generic-proxy reads of the stage before the async-proxy refill
+              issue(t + 1);
+            }
+          }
+          if (!live) continue;
+          uint32_t key = 0, alts = 0;
+          if (act) {
+            const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
+            const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
+            const uint2 ka = sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+            key = ka.x;
+            alts = ka.y;
+          }
+          if (q.wmode) {
+            int wid = -1;
+            uint32_t cf = 1;
+            if (act) {
+              wid = window_id(q, s, pv, cw);
+              if (p.flags) cf = (__ldg(p.flags + s) >> 1) & 1u;
+            }
+            uint32_t rem = __ballot_sync(0xffffffffu, act);
+            while (rem) {
+              const int first = __ffs(rem) - 1;
+              const int idf = __shfl_sync(0xffffffffu, wid, first);
+              if (idf != cur_id) {
+                close_window();
+                cur_id = idf;
+                overflow = pending_skip;
+                pending_skip = false;
+              }
+              const bool mine = act && wid == idf;
+              const uint32_t m = __ballot_sync(0xffffffffu, mine);
+              rem &= ~m;
+              if (cur_id >= 0 && !overflow) {
+                wcount += __popc(m);
+                if (wcount > WCAP) {
+                  overflow = true;
+                } else if (mine) {
+                  if (key != 0 && key != last) {
+                    uint32_t h = (key * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
+                    uint32_t c;
+                    while (true) {  // read first: a shared-memory CAS costs about twice a load or an add
+                      uint32_t e = tab[h];
+                      if (e == EMPTY_KEY) {
+                        e = atomicCAS(tab + h, EMPTY_KEY, (key << KEY_SHIFT) | 1u);
+                        if (e == EMPTY_KEY) { c = 0; break; }
+                      }
+                      if ((e >> KEY_SHIFT) == key) { c = atomicAdd(tab + h, 1u) & F10; break; }
+                      h = (h + 1) & (HASH_SLOTS - 1);
+                    }
+                    if (c) w2 += __ldg(q.dxI + c);
+                    nn += 1u;
+                    m2 = max(m2, c);
+                  }
+                  const uint32_t fa = alts & 0xFFFF, fb = alts >> 16;
+                  bump_half_if(w1a, fa);
+                  bump_half_if(w1b, fb);
+                  nn += (fa ? 1u << 10 : 0u) + (fb ? 1u << 20 : 0u);
+                  cflag += cf;
+                  nall += key != 0;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (q.wmode) close_window();
+    }
+  }
+  __syncthreads();
+  sink_flush(p, sm, cta_group, tid, blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------ finish pass
+struct FinishParams {
+  ScoreParams s;
+  const double* ws;   // window sums of k1_fused
+  int use_smem;       // single background group: 1D ln b tables and the low-count corner of the 2D table in shared memory
+  int cr;             // corner rows = columns (<= CORNER, and only used with narrow records, which carry (k1, k2))
+  int large_ctas;     // CTAs (scratch slabs) of the large-window path
+};
+
+// bin of record r in spectrum `which` (0 = 2D, 1 = 1D pop1, 2 = 1D pop2); 0 = the SNP is not in that likelihood
+__device__ __forceinline__ uint32_t bin_of(const uint2 r, int which, uint32_t last) {
+  if (which == 0) return (r.x != 0 && r.x != last) ? r.x : 0u;
+  return which == 1 ? (r.y & 0xFFFF) : (r.y >> 16);
+}
+
+// sum over the distinct bins of one spectrum of a window (cnt <= WCAP) of x (ln x - ln b), bin by bin as the reference's
+// logpmf difference weighs them: O(cnt^2 / 32) per warp, used only for the windows that must reproduce an exact 0.0
+__device__ __forceinline__ double exact_bins(const ScoreParams& p, int lo, int cnt, int which, const double* lb, int lane) {
+  const uint32_t last = (uint32_t)p.bins2d - 1;
+  double acc = 0.0;
+  for (int ci = 0; ci < cnt; ci += 32) {
+    const int i = ci + lane;
+    const uint32_t ki = i < cnt ? bin_of(load_rec(p.rec, p.fmt, lo + i, p.n1, p.n2, p.C2), which, last) : 0u;
+    uint32_t x = 0;
+    bool earlier = false;
+    for (int cj = 0; cj < cnt; cj += 32) {
+      const int jn = cj + lane;
+      const uint32_t kj = jn < cnt ? bin_of(load_rec(p.rec, p.fmt, lo + jn, p.n1, p.n2, p.C2), which, last) : 0u;
+      for (int t = 0; t < 32; ++t) {
+        const uint32_t kk = __shfl_sync(0xffffffffu, kj, t);
+        const bool eq = kk == ki;
+        x += eq;
+        earlier |= eq && (cj + t < i);
+      }
+    }
+    if (ki && !earlier) acc = fma(u32_to_double(x), (x > 1 ? ln_mult(p, x) : 0.0) - __ldg(lb + ki), acc);
+  }
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(256) k3_finish(const __grid_constant__ FinishParams q) {
+  extern __shared__ __align__(16) double sd[];  // [cr * cr | n1 + 1 | n2 + 1] ln b of group 0
+  const ScoreParams& p = q.s;
+  const int lane = threadIdx.x & 31;
+  const int cr = q.cr;
+  double* s_c = sd;
+  double* s_a = sd + cr * cr;
+  double* s_b = s_a + p.n1 + 1;
+  if (q.use_smem) {
+    for (int i = threadIdx.x; i < cr * cr; i += blockDim.x) s_c[i] = __ldg(p.lb2 + (long long)(i / cr) * p.C2 + (i % cr));
+    for (int i = threadIdx.x; i <= p.n1; i += blockDim.x) s_a[i] = __ldg(p.lb1a + i);
+    for (int i = threadIdx.x; i <= p.n2; i += blockDim.x) s_b[i] = __ldg(p.lb1b + i);
+  }
+  __syncthreads();
+  const uint32_t last = (uint32_t)p.bins2d - 1;
+  const bool narrow = p.fmt.narrow != 0;
+  const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
+  const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
+  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); id < p.ncand; id += nwarp) {
+    const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
+    const int cnt = hi - lo;
+    if (cnt == 0 || cnt > WCAP) continue;  // empty: flagged by K2; large: the CTA path below
+    const int g = p.score_group ? __ldg(p.score_group + __ldg(p.wchrom + id)) : 0;
+    const double* lb2 = p.lb2 + (long long)g * p.bins2d;
+    const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
+    const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
+    const double* Bg = p.B + g * 6;
+    double g2 = 0.0, g1a = 0.0, g1b = 0.0;
+    constexpr int Q = 4;
+    for (int base = 0; base < cnt; base += Q * 32) {
+      double l2[Q], la[Q], lb[Q];
+      if (narrow) {
+        uint32_t r[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          const int i = base + j * 32 + lane;
+          r[j] = i < cnt ? __ldcs(reinterpret_cast<const uint32_t*>(p.rec) + lo + i) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          const int k1 = (int)(r[j] & m1), k2 = (int)((r[j] >> sh2) & m2);
+          const int d1 = (int)((r[j] >> shd1) & md), d2 = (int)(r[j] >> shd2);
+          const uint32_t key = (uint32_t)(k1 * p.C2 + k2);
+          const int fa = folded_interior(k1 + 2 * d1, p.n1), fb = folded_interior(k2 + 2 * d2, p.n2);
+          const bool v2 = key != 0 && key != last;
+          if (q.use_smem) {
+            const bool inc = k1 < cr && k2 < cr;
+            l2[j] = v2 ? (inc ? s_c[k1 * cr + k2] : __ldg(lb2 + key)) : 0.0;
+            la[j] = fa ? s_a[fa] : 0.0;
+            lb[j] = fb ? s_b[fb] : 0.0;
+          } else {
+            l2[j] = v2 ? __ldg(lb2 + key) : 0.0;
+            la[j] = fa ? __ldg(lb1a + fa) : 0.0;
+            lb[j] = fb ? __ldg(lb1b + fb) : 0.0;
+          }
+        }
+      } else {
+        uint2 r[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          const int i = base + j * 32 + lane;
+          r[j] = i < cnt ? __ldcs(reinterpret_cast<const uint2*>(p.rec) + lo + i) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          const uint32_t key = r[j].x, fa = r[j].y & 0xFFFF, fb = r[j].y >> 16;
+          const bool v2 = key != 0 && key != last;
+          l2[j] = v2 ? __ldg(lb2 + key) : 0.0;
+          if (q.use_smem) {
+            la[j] = fa ? s_a[fa] : 0.0;
+            lb[j] = fb ? s_b[fb] : 0.0;
+          } else {
+            la[j] = fa ? __ldg(lb1a + fa) : 0.0;
+            lb[j] = fb ? __ldg(lb1b + fb) : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+    }
+    g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
+    // window sums of the count kernel: lanes 0..2 take one statistic each
+    const double* wsp = q.ws + id * 4;
+    const double bits = __ldg(wsp + 3);
+    const uint32_t nt = (uint32_t)__double2loint(bits), meta = (uint32_t)__double2hiint(bits);
+    const int Nq = lane == 0 ? (int)(nt & 0x3FF) : (lane == 1 ? (int)((nt >> 10) & 0x3FF) : (int)(nt >> 20));
+    const double Wq = lane < 3 ? __ldg(wsp + lane) : 0.0;
+    const double Gq = lane == 0 ? g2 : (lane == 1 ? g1a : g1b);
+    const bool one = lane < 3 && (meta & (WS_ONE_2D << lane)) != 0;
+    const bool own = lane < 3 && Nq > 0 && (double)Nq == __ldg(Bg + lane);  // N == B: possibly the background itself
+    double acc = Wq - Gq;
+    const uint32_t exact = __ballot_sync(0xffffffffu, one || own) & 7u;
+    if (exact) {  // per-bin form for the spectra where the reference's difference of logpmfs is exactly 0.0
+      for (int w = 0; w < 3; ++w)
+        if (exact & (1u << w)) {
+          const double a = exact_bins(p, lo, cnt, w, w == 0 ? lb2 : (w == 1 ? lb1a : lb1b), lane);
+          if (lane == w) acc = a;
+        }
+    }
+    bool none = false;
+    double Tq = 0.0;
+    if (lane < 3) Tq = clr_value(p, Nq, acc, Bg, lane, none);
+    const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
+    if (lane == 0) {
+      uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
+      if (p.snp_mode && !(meta & WS_NALL)) f |= TDSFS_F_SKIPPED;  // :1496 window skipped when its 2D spectrum sums to 0
+      p.r_count[id] = (int)(meta & 0x3FF);
+      p.r_flags[id] = f;
+      p.r_T2[id] = Tq;
+      p.r_n2[id] = Nq;
+    } else if (lane == 1) {
+      p.r_T1a[id] = Tq;
+      p.r_n1a[id] = Nq;
+    } else if (lane == 2) {
+      p.r_T1b[id] = Tq;
+      p.r_n1b[id] = Nq;
+    }
+  }
+  // windows above WCAP SNPs (K2's list, complete before this launch): one CTA each over dense scratch
+  if ((int)blockIdx.x < q.large_ctas && *p.nlarge > 0) score_large_windows(p, blockIdx.x, min((int)gridDim.x, q.large_ctas));
+}
+
+}  // namespace tdsfs

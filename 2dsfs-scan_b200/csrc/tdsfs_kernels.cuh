@@ -30,6 +30,17 @@ constexpr int WCAP = 768;             // windows up to WCAP SNPs are scored by o
 constexpr int LN_TABLE = 4096;        // ln(m) lookup for window multiplicities
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
 
+// Per-SNP record written by the count kernels and read by the scorers.
+//   wide   (uint2):   x = folded 2D bin a1' * (2n2+1) + a2' (0 = contributes nothing),
+//                     y = fa | fb << 16: folded interior 1D bins of pop1 / pop2 (0 = not in that 1D likelihood)
+//   narrow (uint32):  k1 | k2 << b1 | d1 << (b1+b2) | d2 << (b1+b2+md) with (k1, k2) = (a1', a2') the folded 2D cell and
+//                     d = 0 for an unswapped SNP, (2n - alt - ref) / 2 (missing diploids) for a swapped one, so that the
+//                     folded 1D bin is fold(k + 2d) either way (fold(a) = fold(2n - a)).  Half the bytes of the wide form;
+//                     a SNP whose d does not fit `md` bits raises err bit 3 and the pass is redone with wide records.
+struct RecFmt {
+  int narrow, b1, b2, md;
+};
+
 struct KeyParams {
   int n1, n2, fold, C2, bins2d, R1, R2;   // R1 = 2n1+1, R2 = C2 = 2n2+1
   int ns1, ns2, W1, W2;                   // sample columns and uint32 words per population block
@@ -40,8 +51,8 @@ struct KeyParams {
   const uint8_t* flags;
   const tdsfs_fixup_t* fix;
   long long nfix;
-  uint2* rec;         // per SNP: x = folded 2D bin index a1'*(2n2+1)+a2' (0 = contributes nothing),
-                      //          y = fa | fb << 16: folded 1D bins of pop1 / pop2 that enter the 1D likelihoods (0 = none)
+  void* rec;          // per-SNP records (RecFmt)
+  RecFmt fmt;
   uint32_t* hist;     // [group][bins2d | R1 | R2]
   long long gstride;
   const int32_t* bg_group;  // per chromosome -> background group, -1 = not in any background; NULL = uniform_group
@@ -49,7 +60,7 @@ struct KeyParams {
   const long long* chrom_off;
   int C;
   long long bg_lo, bg_hi;   // optional position restriction of the background (-1 = none)
-  int* err;                 // bit0: count out of range
+  int* err;                 // bit0: count out of range, bit2: peer timeout, bit3: narrow record overflow
   int cr, cc;               // corner dims actually used: min(R1, CORNER), min(R2, CORNER)
   int h1a, h1b;             // privatised 1D bins: min(R1, H1CAP), min(R2, H1CAP)
   int nstage, stage_bytes;  // K1 ring: stages of `tile_blocks` 32-SNP blocks; nstage is a multiple of cwarps
@@ -277,6 +288,19 @@ __device__ __forceinline__ int folded_interior(int a, int n) {
   return (a != 0 && f >= 1 && f <= n - 1) ? f : 0;
 }
 
+// narrow record -> (2D bin, fa | fb << 16)
+__device__ __forceinline__ uint2 decode_narrow(uint32_t r, const RecFmt& f, int n1, int n2, int C2) {
+  const int k1 = (int)(r & ((1u << f.b1) - 1u)), k2 = (int)((r >> f.b1) & ((1u << f.b2) - 1u));
+  const int d1 = (int)((r >> (f.b1 + f.b2)) & ((1u << f.md) - 1u)), d2 = (int)(r >> (f.b1 + f.b2 + f.md));
+  return make_uint2((uint32_t)(k1 * C2 + k2),
+                    (uint32_t)folded_interior(k1 + 2 * d1, n1) | ((uint32_t)folded_interior(k2 + 2 * d2, n2) << 16));
+}
+// record s of either format as (2D bin, fa | fb << 16); streamed (read once per pass)
+__device__ __forceinline__ uint2 load_rec(const void* rec, const RecFmt& f, long long s, int n1, int n2, int C2) {
+  if (f.narrow) return decode_narrow(__ldcs(reinterpret_cast<const uint32_t*>(rec) + s), f, n1, n2, C2);
+  return __ldcs(reinterpret_cast<const uint2*>(rec) + s);
+}
+
 // snp_flags handling shared by the count kernels: returns whether the SNP passes the spectrum filters (bit0) and
 // applies the sparse half-call corrections of rows flagged with bit2 (binary search in the sorted fix-up list).
 __device__ __forceinline__ bool row_filters(const KeyParams& p, long long s, int& ref1, int& alt1, int& ref2, int& alt2) {
@@ -296,20 +320,34 @@ __device__ __forceinline__ bool row_filters(const KeyParams& p, long long s, int
   return (f & 1) != 0;
 }
 
-// From the four counts of a SNP to its keys, the output arrays and the background histograms.
-__device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int ref1, int alt1, int ref2, int alt2, int cta_group,
-                                         const SinkSmem& sm, ChromCache& cc) {
+// From the four counts of a SNP to its keys, the output arrays and the background histograms.  Returns (2D bin, fa | fb << 16).
+__device__ __forceinline__ uint2 sink_row(const KeyParams& p, long long s, int ref1, int alt1, int ref2, int alt2, int cta_group,
+                                          const SinkSmem& sm, ChromCache& cc) {
   const bool include = row_filters(p, s, ref1, alt1, ref2, alt2);
-  uint32_t key = 0, alts = 0;
+  uint32_t key = 0, alts = 0, nrec = 0;
   if (include) {
     int k1 = alt1, k2 = alt2;
-    if (p.fold && alt1 + alt2 > p.n1 + p.n2) { k1 = ref1; k2 = ref2; }  // twoDSFS_class.py:199-206
+    const bool swapped = p.fold && alt1 + alt2 > p.n1 + p.n2;
+    if (swapped) { k1 = ref1; k2 = ref2; }  // twoDSFS_class.py:199-206
     if ((unsigned)k1 >= (unsigned)p.R1 || (unsigned)k2 >= (unsigned)p.R2 || (unsigned)alt1 >= (unsigned)p.R1 ||
         (unsigned)alt2 >= (unsigned)p.R2) {
       atomicOr(p.err, 1);
     } else {
       key = (uint32_t)(k1 * p.C2 + k2);  // (0,0) -> 0 : skipped SNP (:212)
       alts = (uint32_t)folded_interior(alt1, p.n1) | ((uint32_t)folded_interior(alt2, p.n2) << 16);
+      if (p.fmt.narrow) {
+        int d1 = 0, d2 = 0;
+        if (swapped) {
+          const int g1 = 2 * p.n1 - alt1 - ref1, g2 = 2 * p.n2 - alt2 - ref2;  // twice the missing diploids
+          d1 = g1 >> 1; d2 = g2 >> 1;
+          if (((g1 | g2) & 1) || g1 < 0 || g2 < 0 || d1 >= (1 << p.fmt.md) || d2 >= (1 << p.fmt.md)) {
+            atomicOr(p.err, 8);  // does not fit the narrow record: the host redoes the pass with wide records
+            d1 = d2 = 0;
+          }
+        }
+        nrec = (uint32_t)k1 | ((uint32_t)k2 << p.fmt.b1) | ((uint32_t)d1 << (p.fmt.b1 + p.fmt.b2)) |
+               ((uint32_t)d2 << (p.fmt.b1 + p.fmt.b2 + p.fmt.md));
+      }
       int g = group_of_row(p, s, cc);
       if (p.debug & 2) g = -1;
       if (g >= 0) {
@@ -329,11 +367,11 @@ __device__ __forceinline__ void sink_row(const KeyParams& p, long long s, int re
       }
     }
   }
-  if (p.debug & 1) {
-    if (key == 0xFFFFFFFFu) __stcs(p.rec + s, make_uint2(key, alts));
-    return;
+  if (!(p.debug & 1)) {  // streaming store: read once by the scorer, from L2 or HBM
+    if (p.fmt.narrow) __stcs(reinterpret_cast<uint32_t*>(p.rec) + s, nrec);
+    else __stcs(reinterpret_cast<uint2*>(p.rec) + s, make_uint2(key, alts));
   }
-  __stcs(p.rec + s, make_uint2(key, alts));  // streaming store: read once by the scorer, from L2 or HBM
+  return make_uint2(key, alts);
 }
 
 // flush the CTA-private histograms of group g into global memory (threads tid..nthr of the sink group)
@@ -877,7 +915,9 @@ __global__ void __launch_bounds__(256) k2_bounds_snp(const __grid_constant__ Win
 
 // ------------------------------------------------------------------------------------------------ K3+K4 scoring
 struct ScoreParams {
-  const uint2* rec;
+  const void* rec;       // per-SNP records (RecFmt)
+  RecFmt fmt;
+  int C2;                // 2 n2 + 1
   const uint8_t* flags;
   const int32_t* wlo;
   const int32_t* whi;
@@ -1043,7 +1083,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const int i = base + q * GT + tg;
-        r[q] = i < cnt ? __ldcs(p.rec + lo + i) : make_uint2(0u, 0u);  // streamed once: keep the ln b table in L2
+        r[q] = i < cnt ? load_rec(p.rec, p.fmt, lo + i, p.n1, p.n2, p.C2) : make_uint2(0u, 0u);  // streamed once: keep the ln b table in L2
         if (has_flags && i < cnt) count += (__ldg(p.flags + lo + i) >> 1) & 1;
       }
 #pragma unroll
@@ -1183,18 +1223,19 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
 }
 
 // One CTA per large window; dense scratch histograms in global memory (L2 resident), cleared by re-walking the window.
+// CTA `cta` of `ncta` (256 threads each, one scratch slab per CTA) takes every ncta-th entry of the large-window list.
 constexpr int LARGE_THREADS = 256;
-__global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_constant__ ScoreParams p) {
+__device__ __forceinline__ void score_large_windows(const ScoreParams& p, int cta, int ncta) {
   __shared__ double red_d[3][LARGE_THREADS / 32];
   __shared__ int red_i[5][LARGE_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nl = *p.nlarge;
   const long long sstride = (long long)p.bins2d + p.n1 + 1 + p.n2 + 1;
-  uint32_t* h2 = p.scratch + (long long)blockIdx.x * sstride;
+  uint32_t* h2 = p.scratch + (long long)cta * sstride;
   uint32_t* h1a = h2 + p.bins2d;
   uint32_t* h1b = h1a + p.n1 + 1;
   const uint32_t last = (uint32_t)p.bins2d - 1;
-  for (int w = blockIdx.x; w < nl; w += gridDim.x) {
+  for (int w = cta; w < nl; w += ncta) {
     const long long id = p.large[w];
     const int lo = p.wlo[id], hi = p.whi[id];
     const int g = p.score_group ? p.score_group[p.wchrom[id]] : 0;
@@ -1204,7 +1245,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint2 r = p.rec[s];
+      const uint2 r = load_rec(p.rec, p.fmt, s, p.n1, p.n2, p.C2);
       const uint32_t k = r.x, a = r.y;
       count += p.flags ? ((p.flags[s] >> 1) & 1) : 1;
       nall += k != 0;
@@ -1216,7 +1257,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     __syncthreads();
     // second walk: the first thread to reach a bin takes its whole count x (atomicExch clears it) and adds x (ln x - ln b)
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
-      const uint2 r = p.rec[s];
+      const uint2 r = load_rec(p.rec, p.fmt, s, p.n1, p.n2, p.C2);
       const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) {
         const uint32_t x = atomicExch(h2 + k, 0u);
@@ -1246,13 +1287,16 @@ __global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_con
     __syncthreads();
   }
 }
+__global__ void __launch_bounds__(LARGE_THREADS) k3_score_large(const __grid_constant__ ScoreParams p) {
+  score_large_windows(p, blockIdx.x, gridDim.x);
+}
 
 // dense spectra of one window (calculate_2d_sfs / calculate_1d_sfs on window_data): 2D bins from the stored records,
 // raw (unfolded) 1D alt counts recomputed from the source rows (counts entry or B32 genotype matrix)
 __global__ void k_window_hist(const __grid_constant__ KeyParams p, int lo, int hi, uint32_t* h2, uint32_t* h1a, uint32_t* h1b) {
   const int RW = p.W1 + p.W2;
   for (long long s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
-    const uint32_t k = p.rec[s].x;
+    const uint32_t k = load_rec(p.rec, p.fmt, s, p.n1, p.n2, p.C2).x;
     if (k) atomicAdd(h2 + k, 1u);
     int ref1, alt1, ref2, alt2;
     if (p.cnt) {

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libtdsfs.so")
 
 BG_NONE, BG_PER_CHROM, BG_GENOME, BG_CHROM = 0, 1, 2, 3
 F_T2D_NONE, F_T1D_P1_NONE, F_T1D_P2_NONE, F_EMPTY, F_SKIPPED = 1, 2, 4, 8, 16
-ERR_ARG, ERR_CUDA, ERR_STATE, ERR_RANGE = 1, 2, 3, 4
+ERR_ARG, ERR_CUDA, ERR_STATE, ERR_RANGE, ERR_RETRY = 1, 2, 3, 4, 5
 
 EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",
@@ -21,7 +21,7 @@ EXPORTS = [
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_close",
-    "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_version",
+    "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_version",
 ]
 
 
@@ -278,3 +278,13 @@ class Handle:
 
     def launch_count(self):
         return int(self._L.tdsfs_launch_count(self._h))
+
+    def scan_info(self):
+        """(fused, record_bytes) of the last scan: fused = the count kernel's window sums + the finish kernel scored it."""
+        f, b = C.c_int32(), C.c_int32()
+        self._check(self._L.tdsfs_scan_info(self._h, C.byref(f), C.byref(b)))
+        return bool(f.value), int(b.value)
+
+    def check(self):
+        """Synchronise and raise on deferred device-side errors (range, peer timeout, record overflow)."""
+        self._check(self._L.tdsfs_check(self._h))

@@ -273,9 +273,8 @@ def run_b200(args, cfg):
     S_total = cfg["S"] if args.scaling == "strong" else cfg["S"] * world
 
     h = T.Handle(local_rank)
-    # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs; above the library's side streams when the
-    # experimental pipelined scorer (TDSFS_PIPELINE=1) needs the count kernel's CTAs placed first
-    stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("TDSFS_PIPELINE", "0") not in ("", "0") else 0)
+    # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs
+    stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     h.set_panel(n1, n2, True)

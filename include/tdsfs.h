@@ -33,8 +33,11 @@ enum {
   TDSFS_ERR_ARG = 1,    /* bad argument / buffer too small */
   TDSFS_ERR_CUDA = 2,   /* CUDA runtime error (message has the cudaError string) */
   TDSFS_ERR_STATE = 3,  /* call order violated (e.g. scan before background) */
-  TDSFS_ERR_RANGE = 4   /* an allele count exceeds 2n of the declared panel: the reference raises KeyError
+  TDSFS_ERR_RANGE = 4,  /* an allele count exceeds 2n of the declared panel: the reference raises KeyError
                            (twoDSFS_class.py:433) for the same input */
+  TDSFS_ERR_RETRY = 5   /* asynchronous pass only: a SNP did not fit the 4-byte per-SNP record; the handle has switched
+                           to 8-byte records and the pass must be run again (synchronous calls and tdsfs_run_bp retry
+                           by themselves) */
 };
 
 /* result flags (per candidate window) */
@@ -207,6 +210,10 @@ int tdsfs_synth_genotypes(tdsfs_t* ctx, void* G_dev, int64_t S, int64_t snp0, in
  * [5]=background call, [6]=scan call, [7]=K1 start -> last score kernel end. */
 int tdsfs_timings(tdsfs_t* ctx, float* ms, int32_t n);
 int64_t tdsfs_launch_count(tdsfs_t* ctx); /* kernels launched by this handle so far */
+/* Which path scored the last scan: *fused = 1 when the fused pair ran (tdsfs_plan_* before tdsfs_background on the
+ * genotype-level entry: the count kernel leaves every window's background-independent sums and one finish kernel gathers
+ * ln b over the per-SNP records), 0 for the table scorer; *record_bytes = 4 (narrow per-SNP record) or 8. */
+int tdsfs_scan_info(tdsfs_t* ctx, int32_t* fused, int32_t* record_bytes);
 int tdsfs_version(void);
 
 #ifdef __cplusplus

@@ -1,4 +1,4 @@
-"""CPU check of the arithmetic behind the experimental pipelined scorer (csrc/tdsfs_pipeline.cuh): the statistic split into a
+"""CPU check of the arithmetic behind the fused scan (csrc/tdsfs_fused.cuh: k1_fused + k3_finish): the statistic split into a
 window-only part W = sum_bins x ln x (accumulated as dx[c] per insert, c = the bin's old count, in any arrival order) and a
 background part G = sum_SNPs ln b[bin], with the per-bin form kept for one-bin windows and for N == B.  Compared with the
 oracle's restatement of the reference likelihood (oracle/sfs_oracle.py clr_dense)."""
@@ -24,16 +24,16 @@ def split_statistic(bins, b):
     lb = np.where(b > 0, np.log(np.maximum(b, 1e-300)), -np.inf)
     seen = {}
     W = 0.0
-    for k in bins:                       # k3a_window_sums: dx of the old count
+    for k in bins:                       # k1_fused: dx of the old count
         c = seen.get(k, 0)
         W += DX[c]
         seen[k] = c + 1
-    G = float(sum(lb[k] for k in bins))  # k3b_gather_finish
+    G = float(sum(lb[k] for k in bins))  # k3_finish
     acc = W - G
-    if len(seen) == 1:                   # one populated bin: x (ln x - ln b) as the table walk computes it
+    if len(seen) == 1:                   # one populated bin: x (ln x - ln b) (exact_bins)
         k = bins[0]
         acc = float(N) * ((LN[N] if N > 1 else 0.0) - lb[k])
-    if float(N) == B:                    # possibly its own background: per-bin form (k3_score_large)
+    if float(N) == B:                    # possibly its own background: per-bin form (exact_bins)
         acc = sum(float(x) * ((LN[x] if x > 1 else 0.0) - lb[k]) for k, x in seen.items())
     t = LN[N] - math.log(B)
     return 2.0 * (acc - float(N) * t)
