@@ -132,9 +132,18 @@ class PackedPanel:
         self.n = 0
         self.last_key_row = -1
         self.n_records = self.n_skipped = 0
+        self.cache_sources = []
 
     def __len__(self):
         return self.n
+
+    def save(self, path, sources=()):
+        """Write the packed panel to disk (save_panel); PackedPanel.load(path) maps it back without re-parsing the VCF."""
+        return save_panel(self, path, sources)
+
+    @staticmethod
+    def load(path, mmap=True):
+        return load_panel(path, mmap)
 
     def check_ranges(self):
         pass
@@ -153,6 +162,111 @@ class PackedPanel:
                 out[f["snp"], 2 * f["pop"]] += f["dref"]
                 out[f["snp"], 2 * f["pop"] + 1] += f["dalt"]
         return out
+
+
+# ----------------------------------------------------------------------------------------------- packed-panel cache
+# On-disk form of a PackedPanel: replaces the reference's pickle + bz2 cache of the parsed dict (scripts/twoDSFS.py:505-510,
+# scripts/src/twoDSFS_class.py:1918-1919).  One file: magic, a JSON header, then the raw arrays at 4096-byte aligned offsets,
+# so that a 13 GB matrix is memory-mapped (np.memmap) instead of re-parsed or copied, and can be uploaded straight from the
+# page cache.
+_CACHE_MAGIC = b"TDSFSPK1"
+_CACHE_ALIGN = 4096
+_FIX_DT = np.dtype([("snp", "<i8"), ("pop", "<i4"), ("dref", "<i4"), ("dalt", "<i4")], align=True)
+
+
+def _source_stamp(paths):
+    out = []
+    for p in paths:
+        st = _os.stat(p)
+        out.append([_os.path.abspath(str(p)), int(st.st_size), int(st.st_mtime_ns)])
+    return out
+
+
+def save_panel(panel, path, sources=()):
+    """Write `panel` to `path` (atomically).  sources: files the panel was built from; their size and mtime are recorded
+    so that cached_pack_vcf can tell a stale cache."""
+    import json
+    vocab, codes = np.unique(np.asarray(panel.ann, dtype=object).astype(str), return_inverse=True) if panel.n else (np.array([], dtype=str), np.zeros(0, np.int64))
+    arrays = {"G": np.ascontiguousarray(panel.G, dtype=np.uint32), "pos": np.ascontiguousarray(panel.pos, dtype=np.int64),
+              "off": np.ascontiguousarray(panel.off, dtype=np.int64), "ann_codes": np.ascontiguousarray(codes, dtype=np.int32),
+              "fixups": np.ascontiguousarray(panel.fixups if panel.fixups is not None else np.zeros(0, _FIX_DT), dtype=_FIX_DT)}
+    header = {"version": 1, "n": int(panel.n), "W1": int(panel.W1), "W2": int(panel.W2), "ns1": int(panel.ns1), "ns2": int(panel.ns2),
+              "chroms": list(panel.chroms), "pops": list(panel.pops), "last_key_row": int(panel.last_key_row),
+              "n_records": int(panel.n_records), "n_skipped": int(panel.n_skipped), "ann_vocab": [str(v) for v in vocab],
+              "sources": _source_stamp(sources), "arrays": {}}
+    # two passes: the header's length decides the first offset
+    offset = 0
+    for _ in range(2):
+        blob = json.dumps(header).encode()
+        offset = (16 + len(blob) + _CACHE_ALIGN - 1) // _CACHE_ALIGN * _CACHE_ALIGN + _CACHE_ALIGN  # slack for the offsets' digits
+        for name, a in arrays.items():
+            header["arrays"][name] = {"offset": offset, "nbytes": int(a.nbytes), "count": int(a.shape[0])}
+            offset = (offset + a.nbytes + _CACHE_ALIGN - 1) // _CACHE_ALIGN * _CACHE_ALIGN
+    blob = json.dumps(header).encode()
+    tmp = str(path) + ".tmp%d" % _os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(_CACHE_MAGIC)
+        f.write(len(blob).to_bytes(8, "little"))
+        f.write(blob)
+        for name, a in arrays.items():
+            f.seek(header["arrays"][name]["offset"])
+            f.write(memoryview(a).cast("B"))
+        f.truncate(max(offset, f.tell()))
+    _os.replace(tmp, str(path))
+    return str(path)
+
+
+def load_panel(path, mmap=True):
+    """Read a PackedPanel written by save_panel.  mmap=True maps the arrays read-only (no copy of the genotype matrix)."""
+    import json
+    with open(path, "rb") as f:
+        if f.read(8) != _CACHE_MAGIC:
+            raise ValueError(f"{path}: not a packed-panel cache")
+        hlen = int.from_bytes(f.read(8), "little")
+        header = json.loads(f.read(hlen).decode())
+    if header.get("version") != 1:
+        raise ValueError(f"{path}: unsupported packed-panel cache version {header.get('version')}")
+
+    def arr(name, dt):
+        meta = header["arrays"][name]
+        if meta["count"] == 0:
+            return np.zeros(0, dtype=dt)
+        if mmap:
+            return np.memmap(path, dtype=dt, mode="r", offset=meta["offset"], shape=(meta["count"],))
+        with open(path, "rb") as f:
+            f.seek(meta["offset"])
+            return np.frombuffer(f.read(meta["nbytes"]), dtype=dt).copy()
+
+    P = PackedPanel()
+    P.n, P.W1, P.W2, P.ns1, P.ns2 = header["n"], header["W1"], header["W2"], header["ns1"], header["ns2"]
+    P.chroms, P.pops, P.last_key_row = list(header["chroms"]), tuple(header["pops"]), header["last_key_row"]
+    P.n_records, P.n_skipped = header["n_records"], header["n_skipped"]
+    P.G = arr("G", np.uint32)
+    P.pos = np.asarray(arr("pos", np.int64))
+    P.off = np.array(arr("off", np.int64))
+    vocab = np.array(header["ann_vocab"], dtype=object)
+    P.ann = vocab[np.asarray(arr("ann_codes", np.int32))] if P.n else np.array([], dtype=object)
+    fx = arr("fixups", _FIX_DT)
+    P.fixups = np.array(fx) if len(fx) else None
+    P.cache_sources = header["sources"]
+    return P
+
+
+def cached_pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, cache_path=None, nthreads=0):
+    """pack_vcf with an on-disk cache next to the VCF (`<vcf>.<pop1>.<pop2>.tdsfspk`): reused while the VCF and the popmap
+    are unchanged (size + mtime), rebuilt otherwise.  The drop-in for `pickle.load(bz2.open(...))` of the reference."""
+    cache_path = cache_path or f"{vcf_filename}.{pop1}.{pop2}.tdsfspk"
+    srcs = (vcf_filename, popinfo_filename)
+    if _os.path.exists(cache_path):
+        try:
+            P = load_panel(cache_path)
+            if P.cache_sources == _source_stamp(srcs) and tuple(P.pops) == (pop1, pop2):
+                return P
+        except (ValueError, KeyError, OSError):
+            pass
+    P = pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, nthreads)
+    save_panel(P, cache_path, srcs)
+    return P
 
 
 def pack_vcf(vcf_filename, popinfo_filename, pop1, pop2, nthreads=0):
@@ -229,7 +343,9 @@ def vcf_to_data_dict(vcf_filename, popinfo_filename, nthreads=0):
 
         pops = L.tdsfs_vcf_counts_pops(h).decode().split("\n")[:-1]
         vocab = L.tdsfs_vcf_counts_vocab(h).decode().split("\n")[:-1]
-        blob = _C.string_at(L.tdsfs_vcf_counts_keys(h), key_bytes).decode() if key_bytes else ""
+        raw = _C.string_at(L.tdsfs_vcf_counts_keys(h), key_bytes) if key_bytes else b""
+        # key_off holds BYTE offsets: a str can be sliced with them only when every character is one byte
+        blob = raw.decode() if raw.isascii() else None
         off = arr(L.tdsfs_vcf_counts_key_off(h), n + 1, np.int64).tolist()
         refalt = _C.string_at(L.tdsfs_vcf_counts_refalt(h), 2 * n).decode() if n else ""
         ann = arr(L.tdsfs_vcf_counts_ann_codes(h), n, np.int32).tolist()
@@ -247,7 +363,8 @@ def vcf_to_data_dict(vcf_filename, popinfo_filename, nthreads=0):
                 calls = {pops[p]: (c[p][0], c[p][1]) for p in order}
             else:
                 calls = {pops[p]: (c[p][0], c[p][1]) for p in order if first[p] < nc}
-            data_dict[blob[off[i]:off[i + 1]]] = {"segregating": (ref, alt), "context": "-" + ref + "-", "calls": calls,
+            key = blob[off[i]:off[i + 1]] if blob is not None else raw[off[i]:off[i + 1]].decode()
+            data_dict[key] = {"segregating": (ref, alt), "context": "-" + ref + "-", "calls": calls,
                                                   "annotation": vocab[ann[i]]}
         return data_dict
     finally:
