@@ -603,10 +603,11 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
       p.cwarps = std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
       if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
+      int depth = 1;  // stages per warp
+      if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, atoi(e));  // tuning knob
       p.nstage = p.cwarps;
       if (old_kernel) {
-        int depth = 1;  // stages per warp
-        if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, std::min(fit / p.cwarps, atoi(e)));  // tuning knob
+        depth = std::max(1, std::min(fit / p.cwarps, depth));
         p.nstage = p.cwarps * depth;
         const int smem = p.nstage * p.stage_bytes + p.nstage * 8 + hist_bytes;
         void (*kern)(KeyParams) = k1_genotypes<0, 0>;
@@ -648,10 +649,18 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
           q.nw1 = q.nw2 = 0;
         }
         q.pos_tma = (((uintptr_t)c->dPos) & 15) == 0 && !getenv("TDSFS_NO_POS_TMA");
-        const int smem = p.cwarps * (stage_stride + q.tab_words * 4) + ((p.cwarps + 1) & ~1) * 8 + hist_words * 4;
-        void (*kern)(FusedParams) = k1_fused<0, 0>;
-        if (c->W1 == 32 && c->W2 == 32) kern = k1_fused<32, 32>;        // 500 + 500 diploids (BASELINE config 5)
-        else if (c->W1 == 14 && c->W2 == 14) kern = k1_fused<14, 14>;   // 200 + 200 diploids (BASELINE config 4)
+        // ring depth: as many stages per warp as asked for and as fit beside the histograms and the window tables
+        const int per_warp_fixed = q.tab_words * 4;
+        while (depth > 1 && p.cwarps * (depth * (stage_stride + 8) + per_warp_fixed) + hist_words * 4 + 16 > smem_max) --depth;
+        p.nstage = p.cwarps * depth;
+        const int smem = p.nstage * stage_stride + p.cwarps * q.tab_words * 4 + ((p.nstage + 1) & ~1) * 8 + hist_words * 4;
+        if (smem > smem_max) return fail(TDSFS_ERR_ARG, "count kernel geometry needs %d bytes of shared memory (warps %d, depth %d)", smem, p.cwarps, depth);
+        // PLAIN instantiation: every per-SNP branch that cannot trigger in the common configuration compiled out
+        const bool plain = !c->dFlags && c->nfix == 0 && p.bg_group == nullptr && p.bg_lo < 0 && c->fold && c->fmt.narrow &&
+                           c->n1 >= 32 && c->n2 >= 32 && c->n1 <= 1023 && c->n2 <= 1023 && !getenv("TDSFS_NO_PLAIN");
+        void (*kern)(FusedParams) = plain ? k1_fused<0, 0, true> : k1_fused<0, 0, false>;
+        if (plain && c->W1 == 32 && c->W2 == 32) kern = k1_fused<32, 32, true>;        // 500 + 500 diploids (BASELINE config 5)
+        else if (plain && c->W1 == 14 && c->W2 == 14) kern = k1_fused<14, 14, true>;   // 200 + 200 diploids (BASELINE config 4)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const long long tile_rows = (long long)p.tile_blocks * BLK;
         for (auto& ch : c->chunks) {
@@ -1083,10 +1092,8 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       memset(&f, 0, sizeof f);
       f.s = s;
       f.ws = c->d_ws;
-      f.cr = c->fmt.narrow ? std::min(CORNER, std::min(c->R1, c->R2)) : 0;
-      const size_t tab_bytes = ((size_t)f.cr * f.cr + c->n1 + 1 + c->n2 + 1) * sizeof(double);
-      f.use_smem = !c->per_chrom_scoring && tab_bytes <= 96 * 1024;
-      if (!f.use_smem) f.cr = 0;
+      const size_t tab_bytes = ((size_t)CORNER * CORNER + 2 * c->n1 + 1 + 2 * c->n2 + 1) * sizeof(double);
+      f.use_smem = c->fmt.narrow && !c->per_chrom_scoring && c->R1 >= CORNER && c->R2 >= CORNER && tab_bytes <= 96 * 1024;
       f.large_ctas = c->large_ctas;
       const int smem = f.use_smem ? (int)tab_bytes : 0;
       CK(cudaFuncSetAttribute(k3_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

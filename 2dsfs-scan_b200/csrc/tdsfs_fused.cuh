@@ -136,7 +136,17 @@ __device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_st
   return min(base + __ffs(b2) - 1, top);
 }
 
-template <int TW1, int TW2>
+// folded bin of a raw alt count, 0 when it does not enter the 1D likelihood (same values as folded_interior, fewer instructions)
+__device__ __forceinline__ uint32_t fold_fast(int a, int n) {
+  const uint32_t f = (uint32_t)min(a, 2 * n - a);
+  return (f - 1u) < (uint32_t)(n - 1) ? f : 0u;
+}
+
+// PLAIN = the common configuration, with every per-SNP branch that cannot trigger compiled out: no snp_flags / fix-ups, one
+// background group for all rows (or none), no position restriction of the background, fold on, 4-byte records, no more
+// sample columns than the declared panel (so no count can leave the spectrum), 32 <= n <= 1023 (the privatised corner is
+// exactly 64 x 64 and every 1D bin is privatised).  Everything else takes the generic instantiation.
+template <int TW1, int TW2, bool PLAIN>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant__ FusedParams q) {
   const KeyParams& p = q.k;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -145,9 +155,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
   const int RW = W1 + W2;
   const int tile_rows = p.tile_blocks * BLK;
   const int stage_stride = p.stage_bytes + tile_rows * 4;  // genotype tile, then the tile's positions
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.cwarps * stage_stride);
+  const int depth = p.nstage / p.cwarps;                   // stages per warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * stage_stride);
   SinkSmem sm;
-  sm.corner = reinterpret_cast<uint32_t*>(full + ((p.cwarps + 1) & ~1));
+  sm.corner = reinterpret_cast<uint32_t*>(full + ((p.nstage + 1) & ~1));
   sm.h1a = sm.corner + p.cr * p.cc;
   sm.h1b = sm.h1a + p.h1a;
   const int nhist = p.cr * p.cc + p.h1a + p.h1b;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
   uint32_t* w1b = w1a + q.nw1;
 
   if (tid == 0) {
-    for (int i = 0; i < p.cwarps; ++i) mbar_init(full + i, 1);
+    for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
   }
   for (int i = tid; i < nhist; i += blockDim.x) sm.corner[i] = 0;
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
     return max(r0, (int)(t / tile_rows * tile_rows));
   };
   ChromCache cc;
-  const int cta_group = tile_group(p, target(blockIdx.x * p.cwarps), cc);
+  const int cta_group = PLAIN ? p.uniform_group : tile_group(p, target(blockIdx.x * p.cwarps), cc);
 
   if (warp < p.cwarps) {
     const int j = blockIdx.x * p.cwarps + warp;
@@ -184,24 +195,27 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
     const int slo = snap_row(q, target(j), st0, lane);
     const int shi = snap_row(q, target(j + 1), st1, lane);
     if (slo < shi) {
-      uint8_t* stage = smem + (size_t)warp * stage_stride;
-      const int* spos = reinterpret_cast<const int*>(stage + p.stage_bytes);
-      uint64_t* bar = full + warp;
+      uint8_t* stages = smem + (size_t)warp * depth * stage_stride;
+      uint64_t* bars = full + warp * depth;
       const long long block_words = (long long)RW * BLK;
       const int b_end = (r1 + BLK - 1) / BLK;  // blocks this launch may read (later ones may still be uploading)
       const int S4 = S & ~3;                   // positions below S4 come through TMA in whole 16-byte groups
       const int t_begin = slo / tile_rows, t_end = (shi - 1) / tile_rows + 1;
-      auto issue = [&](int t) {  // lane 0 only
+      auto issue = [&](int t, int slot) {  // lane 0 only
         const int blk0 = t * p.tile_blocks;
         const int nb = min(p.tile_blocks, b_end - blk0);
         const uint32_t gbytes = (uint32_t)(nb * block_words * 4);
         uint32_t pbytes = 0;
         if (q.pos_tma) pbytes = (uint32_t)max(0, min(nb * BLK, S4 - blk0 * BLK)) * 4u;
-        mbar_arrive_expect_tx(bar, gbytes + pbytes);
-        bulk_g2s_stream(stage, p.G + (long long)blk0 * block_words, gbytes, bar);
-        if (pbytes) bulk_g2s(stage + p.stage_bytes, p.pos + (long long)blk0 * BLK, pbytes, bar);
+        uint8_t* stage = stages + (size_t)slot * stage_stride;
+        mbar_arrive_expect_tx(bars + slot, gbytes + pbytes);
+        bulk_g2s_stream(stage, p.G + (long long)blk0 * block_words, gbytes, bars + slot);
+        if (pbytes) bulk_g2s(stage + p.stage_bytes, p.pos + (long long)blk0 * BLK, pbytes, bars + slot);
       };
-      if (lane == 0) issue(t_begin);
+      if (lane == 0)
+        for (int d = 0; d < depth; ++d)
+          if (t_begin + d < t_end) issue(t_begin + d, d);
+      int slot = 0;
       uint32_t ph = 0;
 
       // ---- state of the window the warp is in
@@ -209,8 +223,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
       bool overflow = false;           // the window is not summed here (more than WCAP SNPs, or entered mid-way)
       bool pending_skip = !st0;
       int wcount = 0;
+      int win_end_pos = 0, win_end_row = 0;  // rows below win_end_row at positions below win_end_pos are in window cur_id
       double w2 = 0.0;
-      uint32_t nn = 0, m2 = 0, cflag = 0, nall = 0;
+      uint32_t nn = 0;                 // N2 | N1a << 10 | N1b << 20 (this lane's share)
+      uint32_t aux = 0;                // distinct 2D bins | SNPs with a 2D key << 10 | count_snps flags << 20
       ChromWin cw;
       const uint32_t last = (uint32_t)p.bins2d - 1;
       constexpr uint32_t F10 = (1u << KEY_SHIFT) - 1;
@@ -220,15 +236,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
         if (cur_id >= 0) {
           if (!overflow) {
             double a1 = 0.0, b1 = 0.0;
-            uint32_t ma = 0, mb = 0;
+            uint32_t dd = 0;  // distinct folded 1D bins: pop1 | pop2 << 10
             for (int i = lane; i < q.nw1; i += 32) {
               const uint32_t v = w1a[i];
               if (v) {
                 w1a[i] = 0;
                 const uint32_t x0 = v & 0xFFFF, x1 = v >> 16;
-                if (x0 > 1) a1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), a1);
-                if (x1 > 1) a1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), a1);
-                ma = max(ma, max(x0, x1));
+                a1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), a1);  // ln 0 and ln 1 are stored as 0
+                a1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), a1);
+                dd += (x0 != 0) + (x1 != 0);
               }
             }
             for (int i = lane; i < q.nw2; i += 32) {
@@ -236,23 +252,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
               if (v) {
                 w1b[i] = 0;
                 const uint32_t x0 = v & 0xFFFF, x1 = v >> 16;
-                if (x0 > 1) b1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), b1);
-                if (x1 > 1) b1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), b1);
-                mb = max(mb, max(x0, x1));
+                b1 = fma(u32_to_double(x0), __ldg(q.lnI + x0), b1);
+                b1 = fma(u32_to_double(x1), __ldg(q.lnI + x1), b1);
+                dd += ((x0 != 0) + (x1 != 0)) << 10;
               }
             }
             const uint32_t nt = __reduce_add_sync(0xffffffffu, nn);
-            const uint32_t m2t = __reduce_max_sync(0xffffffffu, m2);
-            ma = __reduce_max_sync(0xffffffffu, ma);
-            mb = __reduce_max_sync(0xffffffffu, mb);
-            const uint32_t cft = __reduce_add_sync(0xffffffffu, cflag);
-            const uint32_t nat = __reduce_add_sync(0xffffffffu, nall);
+            const uint32_t at = __reduce_add_sync(0xffffffffu, aux);
+            const uint32_t dt = __reduce_add_sync(0xffffffffu, dd);
             const double w2t = warp_sum(w2);
             a1 = warp_sum(a1);
             b1 = warp_sum(b1);
-            const uint32_t N2 = nt & F10, N1a = (nt >> 10) & F10, N1b = nt >> 20;
-            const uint32_t meta = cft | (N2 && m2t + 1 == N2 ? WS_ONE_2D : 0u) | (N1a && ma == N1a ? WS_ONE_1A : 0u) |
-                                  (N1b && mb == N1b ? WS_ONE_1B : 0u) | (nat ? WS_NALL : 0u);
+            const uint32_t cft = PLAIN ? (uint32_t)wcount : (at >> 20);
+            const uint32_t meta = cft | ((at & F10) == 1u ? WS_ONE_2D : 0u) | ((dt & F10) == 1u ? WS_ONE_1A : 0u) |
+                                  ((dt >> 10) == 1u ? WS_ONE_1B : 0u) | (((at >> 10) & F10) ? WS_NALL : 0u);
             if (lane < 4) {
               const double v = lane == 0 ? w2t : (lane == 1 ? a1 : (lane == 2 ? b1 : __hiloint2double((int)meta, (int)nt)));
               q.ws[(long long)cur_id * 4 + lane] = v;
@@ -265,22 +278,44 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
           for (int i = 0; i < HASH_SLOTS / 128; ++i) t4[lane + i * 32] = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
         }
         w2 = 0.0;
-        nn = m2 = cflag = nall = 0;
+        nn = aux = 0;
         wcount = 0;
         __syncwarp();
+      };
+
+      // this lane's SNP enters the current window's tables (2D: the insert returns the bin's old count c)
+      auto insert = [&](uint32_t key, uint32_t fa, uint32_t fb, uint32_t cf) {
+        if (key != 0 && key != last) {
+          uint32_t h = (key * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
+          const uint32_t fresh = (key << KEY_SHIFT) | 1u;
+          uint32_t c;
+          while (true) {  // most bins of a window are new: try to claim the slot first
+            const uint32_t e = atomicCAS(tab + h, EMPTY_KEY, fresh);
+            if (e == EMPTY_KEY) { c = 0; break; }
+            if ((e >> KEY_SHIFT) == key) { c = atomicAdd(tab + h, 1u) & F10; break; }
+            h = (h + 1) & (HASH_SLOTS - 1);
+          }
+          if (c) w2 += __ldg(q.dxI + c);
+          nn += 1u;
+          aux += c == 0;
+        }
+        bump_half_if(w1a, fa);
+        bump_half_if(w1b, fb);
+        nn += (fa ? 1u << 10 : 0u) + (fb ? 1u << 20 : 0u);
+        aux += (key != 0 ? 1u << 10 : 0u) + (PLAIN ? 0u : cf << 20);
       };
 
       for (int t = t_begin; t < t_end; ++t) {
         const int blk0 = t * p.tile_blocks;
         const int nb = min(p.tile_blocks, b_end - blk0);
-        mbar_wait(bar, ph);
-        ph ^= 1;
+        mbar_wait(bars + slot, ph);
+        const uint8_t* stage = stages + (size_t)slot * stage_stride;
         const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+        const int* spos = reinterpret_cast<const int*>(stage + p.stage_bytes);
         for (int b = 0; b < nb; ++b) {
           const int sb = (blk0 + b) * BLK;
           const int s = sb + lane;
           const bool live = sb + BLK > slo && sb < shi;  // warp-uniform: the block holds rows of this warp's range
-          const bool act = s >= slo && s < shi;
           uint32_t T1 = 0, M1 = 0, T2 = 0, M2 = 0;
           int pv = 0;
           if (live) {
@@ -291,7 +326,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
               count_block_b32<TW1>(rowp, W1, T1, M1);
               count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
             }
-            if (q.wmode == 1 || p.bg_lo >= 0) {
+            if (q.wmode == 1) {
               if (q.pos_tma && s < S4) pv = spos[b * BLK + lane];
               else if (s < S) pv = __ldg(p.pos + s);
             }
@@ -300,72 +335,99 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
             // the stage has been read completely: refill it BEFORE the fold / record / histogram / window work of its
             // last block, so that work overlaps the next load instead of delaying it
             __syncwarp();
-            if (lane == 0 && t + 1 < t_end) {
+            if (lane == 0 && t + depth < t_end) {
               fence_proxy_async();  // order this warp's generic-proxy reads of the stage before the async-proxy refill
-              issue(t + 1);
+              issue(t + depth, slot);
             }
           }
           if (!live) continue;
-          uint32_t key = 0, alts = 0;
+          const bool whole = sb >= slo && sb + BLK <= shi;  // every lane's row belongs to this warp
+          const bool act = whole || (s >= slo && s < shi);
+          uint32_t key = 0, fa = 0, fb = 0, cf = 1;
           if (act) {
             const int alt1 = (int)(T1 - M1), alt2 = (int)(T2 - M2);
             const int ref1 = 2 * (p.ns1 - (int)M1) - alt1, ref2 = 2 * (p.ns2 - (int)M2) - alt2;
-            const uint2 ka = sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
-            key = ka.x;
-            alts = ka.y;
-          }
-          if (q.wmode) {
-            int wid = -1;
-            uint32_t cf = 1;
-            if (act) {
-              wid = window_id(q, s, pv, cw);
+            if (PLAIN) {
+              const bool swapped = alt1 + alt2 > p.n1 + p.n2;  // joint fold, twoDSFS_class.py:199-206
+              const int k1 = swapped ? ref1 : alt1, k2 = swapped ? ref2 : alt2;
+              int d1 = swapped ? (p.n1 - p.ns1) + (int)M1 : 0, d2 = swapped ? (p.n2 - p.ns2) + (int)M2 : 0;
+              if ((d1 | d2) >> p.fmt.md) {  // does not fit the narrow record: the host redoes the pass with wide records
+                atomicOr(p.err, 8);
+                d1 = d2 = 0;
+              }
+              key = (uint32_t)(k1 * p.C2 + k2);  // (0,0) -> 0 : skipped SNP (:212)
+              __stcs(reinterpret_cast<uint32_t*>(p.rec) + s,
+                     (uint32_t)k1 | ((uint32_t)k2 << p.fmt.b1) | ((uint32_t)d1 << (p.fmt.b1 + p.fmt.b2)) |
+                         ((uint32_t)d2 << (p.fmt.b1 + p.fmt.b2 + p.fmt.md)));
+              fa = fold_fast(alt1, p.n1);
+              fb = fold_fast(alt2, p.n2);
+              if (cta_group >= 0) {  // background: privatised 64 x 64 corner and 1D bins, the rest straight to global memory
+                if (key) {
+                  if ((k1 | k2) < CORNER) atomicAdd(sm.corner + (k1 << 6 | k2), 1u);
+                  else atomicAdd(p.hist + key, 1u);
+                }
+                if (alt1) atomicAdd(sm.h1a + alt1, 1u);
+                if (alt2) atomicAdd(sm.h1b + alt2, 1u);
+              }
+            } else {
+              const uint2 ka = sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
+              key = ka.x;
+              fa = ka.y & 0xFFFF;
+              fb = ka.y >> 16;
               if (p.flags) cf = (__ldg(p.flags + s) >> 1) & 1u;
             }
-            uint32_t rem = __ballot_sync(0xffffffffu, act);
-            while (rem) {
-              const int first = __ffs(rem) - 1;
-              const int idf = __shfl_sync(0xffffffffu, wid, first);
-              if (idf != cur_id) {
-                close_window();
-                cur_id = idf;
-                overflow = pending_skip;
-                pending_skip = false;
-              }
-              const bool mine = act && wid == idf;
-              const uint32_t m = __ballot_sync(0xffffffffu, mine);
-              rem &= ~m;
-              if (cur_id >= 0 && !overflow) {
-                wcount += __popc(m);
-                if (wcount > WCAP) {
-                  overflow = true;
-                } else if (mine) {
-                  if (key != 0 && key != last) {
-                    uint32_t h = (key * 0x9E3779B1u) >> 22;  // HASH_SLOTS = 2^10
-                    uint32_t c;
-                    while (true) {  // read first: a shared-memory CAS costs about twice a load or an add
-                      uint32_t e = tab[h];
-                      if (e == EMPTY_KEY) {
-                        e = atomicCAS(tab + h, EMPTY_KEY, (key << KEY_SHIFT) | 1u);
-                        if (e == EMPTY_KEY) { c = 0; break; }
-                      }
-                      if ((e >> KEY_SHIFT) == key) { c = atomicAdd(tab + h, 1u) & F10; break; }
-                      h = (h + 1) & (HASH_SLOTS - 1);
-                    }
-                    if (c) w2 += __ldg(q.dxI + c);
-                    nn += 1u;
-                    m2 = max(m2, c);
-                  }
-                  const uint32_t fa = alts & 0xFFFF, fb = alts >> 16;
-                  bump_half_if(w1a, fa);
-                  bump_half_if(w1b, fb);
-                  nn += (fa ? 1u << 10 : 0u) + (fb ? 1u << 20 : 0u);
-                  cflag += cf;
-                  nall += key != 0;
-                }
-              }
+          }
+          if (!q.wmode) continue;
+          // ---- window stage.  Fast path: every row of the block lies in the window the warp is already in
+          if (whole && cur_id >= 0 && __all_sync(0xffffffffu, pv < win_end_pos && s < win_end_row)) {
+            if (!overflow) {
+              wcount += BLK;
+              if (wcount > WCAP) overflow = true;
+              else insert(key, fa, fb, cf);
+            }
+            continue;
+          }
+          int wid = -1;
+          if (act) wid = window_id(q, s, pv, cw);
+          uint32_t rem = __ballot_sync(0xffffffffu, act);
+          while (rem) {
+            const int first = __ffs(rem) - 1;
+            const int idf = __shfl_sync(0xffffffffu, wid, first);
+            if (idf != cur_id) {
+              close_window();
+              cur_id = idf;
+              overflow = pending_skip;
+              pending_skip = false;
+            }
+            const bool mine = act && wid == idf;
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            rem &= ~m;
+            if (cur_id >= 0 && !overflow) {
+              wcount += __popc(m);
+              if (wcount > WCAP) overflow = true;
+              else if (mine) insert(key, fa, fb, cf);
+            }
+          }
+          // extent of the window the warp is in now (that of the block's last active row)
+          {
+            const uint32_t am = __ballot_sync(0xffffffffu, act);
+            const int src = 31 - __clz((int)am);  // am != 0: the block is live
+            const int c_lo = __shfl_sync(0xffffffffu, cw.lo, src), c_hi = __shfl_sync(0xffffffffu, cw.hi, src);
+            const int c_base = __shfl_sync(0xffffffffu, cw.cbase, src);
+            if (cur_id < 0) {
+              win_end_pos = 0;  // outside every window: keep taking the general path
+              win_end_row = 0;
+            } else if (q.wmode == 1) {
+              const long long e = 1 + (long long)(cur_id - c_base + 1) * (long long)q.W;
+              win_end_pos = e > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int)e;
+              win_end_row = c_hi;
+            } else {
+              win_end_pos = 0x7FFFFFFF;
+              win_end_row = c_lo + (cur_id - c_base + 1) * (int)q.W;
             }
           }
         }
+        if (++slot == depth) { slot = 0; ph ^= 1; }
       }
       if (q.wmode) close_window();
     }
@@ -378,8 +440,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
 struct FinishParams {
   ScoreParams s;
   const double* ws;   // window sums of k1_fused
-  int use_smem;       // single background group: 1D ln b tables and the low-count corner of the 2D table in shared memory
-  int cr;             // corner rows = columns (<= CORNER, and only used with narrow records, which carry (k1, k2))
+  int use_smem;       // narrow records + one background group + a spectrum of at least 64 x 64: ln b tables in shared memory
   int large_ctas;     // CTAs (scratch slabs) of the large-window path
 };
 
@@ -415,21 +476,23 @@ __device__ __forceinline__ double exact_bins(const ScoreParams& p, int lo, int c
 }
 
 __global__ void __launch_bounds__(256) k3_finish(const __grid_constant__ FinishParams q) {
-  extern __shared__ __align__(16) double sd[];  // [cr * cr | n1 + 1 | n2 + 1] ln b of group 0
+  // ln b of group 0 staged per CTA: [cr * cr] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
+  // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
+  // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch
+  extern __shared__ __align__(16) double sd[];
   const ScoreParams& p = q.s;
   const int lane = threadIdx.x & 31;
-  const int cr = q.cr;
+  const bool fast = q.use_smem != 0;  // host: narrow records, one background group, spectrum at least 64 x 64
   double* s_c = sd;
-  double* s_a = sd + cr * cr;
-  double* s_b = s_a + p.n1 + 1;
-  if (q.use_smem) {
-    for (int i = threadIdx.x; i < cr * cr; i += blockDim.x) s_c[i] = __ldg(p.lb2 + (long long)(i / cr) * p.C2 + (i % cr));
-    for (int i = threadIdx.x; i <= p.n1; i += blockDim.x) s_a[i] = __ldg(p.lb1a + i);
-    for (int i = threadIdx.x; i <= p.n2; i += blockDim.x) s_b[i] = __ldg(p.lb1b + i);
+  double* s_a = sd + CORNER * CORNER;
+  double* s_b = s_a + 2 * p.n1 + 1;
+  if (fast) {
+    for (int i = threadIdx.x; i < CORNER * CORNER; i += blockDim.x) s_c[i] = i ? __ldg(p.lb2 + (long long)(i >> 6) * p.C2 + (i & 63)) : 0.0;
+    for (int i = threadIdx.x; i <= 2 * p.n1; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n1); s_a[i] = f ? __ldg(p.lb1a + f) : 0.0; }
+    for (int i = threadIdx.x; i <= 2 * p.n2; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n2); s_b[i] = f ? __ldg(p.lb1b + f) : 0.0; }
   }
   __syncthreads();
   const uint32_t last = (uint32_t)p.bins2d - 1;
-  const bool narrow = p.fmt.narrow != 0;
   const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
   const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
@@ -443,57 +506,53 @@ __global__ void __launch_bounds__(256) k3_finish(const __grid_constant__ FinishP
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
     const double* Bg = p.B + g * 6;
     double g2 = 0.0, g1a = 0.0, g1b = 0.0;
-    constexpr int Q = 4;
-    for (int base = 0; base < cnt; base += Q * 32) {
-      double l2[Q], la[Q], lb[Q];
-      if (narrow) {
+    if (fast) {
+      constexpr int Q = 8;  // records per lane in flight
+      const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec) + lo;
+      for (int base = 0; base < cnt; base += Q * 32) {
         uint32_t r[Q];
+        double l2[Q], la[Q], lb[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
           const int i = base + j * 32 + lane;
-          r[j] = i < cnt ? __ldcs(reinterpret_cast<const uint32_t*>(p.rec) + lo + i) : 0u;
+          r[j] = i < cnt ? __ldcs(rec + i) : 0u;  // 0 decodes to the skipped bin: every table holds 0 there
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-          const int k1 = (int)(r[j] & m1), k2 = (int)((r[j] >> sh2) & m2);
-          const int d1 = (int)((r[j] >> shd1) & md), d2 = (int)(r[j] >> shd2);
-          const uint32_t key = (uint32_t)(k1 * p.C2 + k2);
-          const int fa = folded_interior(k1 + 2 * d1, p.n1), fb = folded_interior(k2 + 2 * d2, p.n2);
-          const bool v2 = key != 0 && key != last;
-          if (q.use_smem) {
-            const bool inc = k1 < cr && k2 < cr;
-            l2[j] = v2 ? (inc ? s_c[k1 * cr + k2] : __ldg(lb2 + key)) : 0.0;
-            la[j] = fa ? s_a[fa] : 0.0;
-            lb[j] = fb ? s_b[fb] : 0.0;
+          const uint32_t k1 = r[j] & m1, k2 = (r[j] >> sh2) & m2;
+          const uint32_t a1 = k1 + 2u * ((r[j] >> shd1) & md), a2 = k2 + 2u * (r[j] >> shd2);
+          if ((k1 | k2) < (uint32_t)CORNER) {
+            l2[j] = s_c[(k1 << 6) | k2];
           } else {
-            l2[j] = v2 ? __ldg(lb2 + key) : 0.0;
-            la[j] = fa ? __ldg(lb1a + fa) : 0.0;
-            lb[j] = fb ? __ldg(lb1b + fb) : 0.0;
+            const uint32_t key = k1 * (uint32_t)p.C2 + k2;
+            l2[j] = key != last ? __ldg(lb2 + key) : 0.0;
           }
+          la[j] = s_a[a1];
+          lb[j] = s_b[a2];
         }
-      } else {
+#pragma unroll
+        for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+      }
+    } else {
+      constexpr int Q = 4;
+      for (int base = 0; base < cnt; base += Q * 32) {
         uint2 r[Q];
+        double l2[Q], la[Q], lb[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
           const int i = base + j * 32 + lane;
-          r[j] = i < cnt ? __ldcs(reinterpret_cast<const uint2*>(p.rec) + lo + i) : make_uint2(0u, 0u);
+          r[j] = i < cnt ? load_rec(p.rec, p.fmt, lo + i, p.n1, p.n2, p.C2) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
           const uint32_t key = r[j].x, fa = r[j].y & 0xFFFF, fb = r[j].y >> 16;
-          const bool v2 = key != 0 && key != last;
-          l2[j] = v2 ? __ldg(lb2 + key) : 0.0;
-          if (q.use_smem) {
-            la[j] = fa ? s_a[fa] : 0.0;
-            lb[j] = fb ? s_b[fb] : 0.0;
-          } else {
-            la[j] = fa ? __ldg(lb1a + fa) : 0.0;
-            lb[j] = fb ? __ldg(lb1b + fb) : 0.0;
-          }
+          l2[j] = (key != 0 && key != last) ? __ldg(lb2 + key) : 0.0;
+          la[j] = fa ? __ldg(lb1a + fa) : 0.0;
+          lb[j] = fb ? __ldg(lb1b + fb) : 0.0;
         }
-      }
 #pragma unroll
-      for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+        for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+      }
     }
     g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
     // window sums of the count kernel: lanes 0..2 take one statistic each
