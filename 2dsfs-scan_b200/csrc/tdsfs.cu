@@ -66,6 +66,7 @@ struct tdsfs_ctx {
   bool own_cnt = false;
   const int32_t* dPos = nullptr;
   bool own_pos = false;
+  bool loaded = false;     // a (possibly empty) data set is loaded
   const uint8_t* dFlags = nullptr;
   bool own_flags = false;
   tdsfs_fixup_t* dFix = nullptr;
@@ -238,6 +239,7 @@ static int pool_get(void** pool, size_t* cap, size_t bytes, void** out) {
 static void free_data(tdsfs_ctx* c) {
   c->dG = nullptr; c->dCnt = nullptr; c->dPos = nullptr; c->dFlags = nullptr;
   c->own_G = c->own_cnt = c->own_pos = c->own_flags = false;
+  c->loaded = false;
   dev_free(c->dFix);
   c->nfix = 0;
   dev_free(c->d_off);
@@ -331,7 +333,8 @@ static int adopt_or_upload(tdsfs_ctx* c, const T* src, long long n, const T** ds
 static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long long* chrom_off, int C, const uint8_t* flags,
                        bool need_flag_copy) {
   if (S < 0 || S > 0x7FFFFF00LL) return fail(TDSFS_ERR_ARG, "S = %lld out of range", S);
-  if (C < 1 || !chrom_off || !pos) return fail(TDSFS_ERR_ARG, "pos / chrom_off missing or C < 1");
+  if (C < 0 || !chrom_off || (!pos && S > 0)) return fail(TDSFS_ERR_ARG, "pos / chrom_off missing or C < 0");
+  if (C == 0 && S != 0) return fail(TDSFS_ERR_ARG, "no chromosomes but S = %lld", S);
   if (chrom_off[0] != 0 || chrom_off[C] != S) return fail(TDSFS_ERR_ARG, "chrom_off must start at 0 and end at S");
   for (int i = 0; i < C; ++i)
     if (chrom_off[i + 1] < chrom_off[i]) return fail(TDSFS_ERR_ARG, "chrom_off not monotone");
@@ -340,8 +343,14 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
   c->h_off.assign(chrom_off, chrom_off + C + 1);
   CKR(dev_alloc(&c->d_off, C + 1));
   CK(cudaMemcpyAsync(c->d_off, chrom_off, (size_t)(C + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-  CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos, &c->pool_pos, &c->cap_pos));
-  if (flags) {
+  if (S > 0) CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos, &c->pool_pos, &c->cap_pos));
+  else {  // an empty shard (a rank of a sharded scan with no rows): a valid, empty position array
+    void* d = nullptr;
+    CKR(pool_get(&c->pool_pos, &c->cap_pos, 256, &d));
+    c->dPos = (const int32_t*)d;
+    c->own_pos = true;
+  }
+  if (flags && S > 0) {
     if (need_flag_copy && is_device_ptr(flags)) {
       void* d = nullptr;
       CKR(pool_get(&c->pool_flags, &c->cap_flags, (size_t)S, &d));
@@ -377,20 +386,23 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
 
 extern "C" int tdsfs_load_counts(tdsfs_t* c, const uint16_t* cnt, int64_t S, const int32_t* pos, const int64_t* chrom_off,
                                  int32_t C, const uint8_t* snp_flags) {
-  if (!c || !cnt) return fail(TDSFS_ERR_ARG, "ctx / cnt is NULL");
+  if (!c || (!cnt && S > 0)) return fail(TDSFS_ERR_ARG, "ctx / cnt is NULL");
   if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
   CK(cudaSetDevice(c->device));
   free_data(c);
   CKR(load_common(c, S, pos, (const long long*)chrom_off, C, snp_flags, false));
-  CKR(adopt_or_upload(c, cnt, S * 4, &c->dCnt, &c->own_cnt, &c->pool_cnt, &c->cap_cnt));
-  if (((uintptr_t)c->dCnt & 7) != 0) return fail(TDSFS_ERR_ARG, "cnt must be 8-byte aligned");
+  if (S > 0) {
+    CKR(adopt_or_upload(c, cnt, S * 4, &c->dCnt, &c->own_cnt, &c->pool_cnt, &c->cap_cnt));
+    if (((uintptr_t)c->dCnt & 7) != 0) return fail(TDSFS_ERR_ARG, "cnt must be 8-byte aligned");
+  }
+  c->loaded = true;
   return finish(c);
 }
 
 extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_t words1, int32_t words2, int32_t ns1,
                                     int32_t ns2, const int32_t* pos, const int64_t* chrom_off, int32_t C,
                                     const tdsfs_fixup_t* fixups, int64_t n_fixups, const uint8_t* snp_flags) {
-  if (!c || !G) return fail(TDSFS_ERR_ARG, "ctx / G is NULL");
+  if (!c || (!G && S > 0)) return fail(TDSFS_ERR_ARG, "ctx / G is NULL");
   if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
   if (words1 < 2 || words2 < 2 || (words1 & 1) || (words2 & 1) || ns1 < 0 || ns2 < 0 || ns1 > words1 * 16 || ns2 > words2 * 16)
     return fail(TDSFS_ERR_ARG, "bad genotype geometry (words %d/%d, samples %d/%d): a population is an even number of words, 32 samples per (lo, hi) pair",
@@ -428,6 +440,11 @@ extern "C" int tdsfs_load_genotypes(tdsfs_t* c, const void* G, int64_t S, int32_
     CK(cudaMemcpyAsync(c->dFix, hf.data(), (size_t)n_fixups * sizeof(tdsfs_fixup_t), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->nfix = n_fixups;
+  }
+  c->loaded = true;
+  if (S == 0) {
+    c->chunks.push_back({0, 0, nullptr});
+    return finish(c);
   }
   if (is_device_ptr(G)) {
     if (((uintptr_t)G & 15) != 0) return fail(TDSFS_ERR_ARG, "device G must be 16-byte aligned");
@@ -489,9 +506,11 @@ static void fill_key_params(tdsfs_ctx* c, KeyParams& p) {
 
 extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int64_t bg_lo, int64_t bg_hi) {
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
-  if (!c->dG && !c->dCnt) return fail(TDSFS_ERR_STATE, "load data first");
+  if (!c->loaded) return fail(TDSFS_ERR_STATE, "load data first");
   if (mode < TDSFS_BG_NONE || mode > TDSFS_BG_CHROM) return fail(TDSFS_ERR_ARG, "bad background mode %d", mode);
-  if (mode == TDSFS_BG_CHROM && (bg_chrom < 0 || bg_chrom >= c->C)) return fail(TDSFS_ERR_ARG, "background chromosome %d out of range", bg_chrom);
+  // bg_chrom = -1: none of this handle's chromosomes is in the background (a rank of a sharded scan that does not own the
+  // background chromosome): the single-group histogram is still allocated and zeroed so that it can take part in the sum
+  if (mode == TDSFS_BG_CHROM && (bg_chrom < -1 || bg_chrom >= c->C)) return fail(TDSFS_ERR_ARG, "background chromosome %d out of range", bg_chrom);
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   CKR(peer_settle(c));  // peers may still be pushing the previous exchange into the histogram
@@ -581,7 +600,9 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       // Ring geometry (measured, profiles/README.md "K1 ring geometry"): ONE stage per warp and about 128 KB of tiles in
       // flight per SM.  Rows up to 8 KB per block use two-block tiles; more warps for narrow rows (more per-SNP work per
       // byte), fewer and larger requests for wide rows.  Deeper rings and more bytes in flight are slower on B200.
-      p.tile_blocks = blk_bytes <= 8192 ? std::max(2, 8192 / blk_bytes) : 1;  // one TMA bulk copy per tile
+      // fused kernel (measured, profiles/README.md round 2): as many warps as fit (it is bound by per-warp instruction latency,
+      // not by bytes in flight) with tiles of about 8 KB; the plain count kernel keeps the round-1 rule (128 KB in flight)
+      p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile
       if (const char* e = getenv("TDSFS_K1_TILE")) p.tile_blocks = std::max(1, atoi(e));  // tuning knob: blocks per tile
       p.stage_bytes = p.tile_blocks * blk_bytes;
       const bool old_kernel = getenv("TDSFS_K1_OLD") != nullptr || getenv("TDSFS_K1_PROBE") != nullptr;  // A/B + bandwidth probe
@@ -601,7 +622,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
         fit = (smem_max - hist_words * 4 - 16) / (stage_stride + 8);
       }
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
-      p.cwarps = std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
+      p.cwarps = fuse ? std::min(fit, K1_CWARPS) : std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
       if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
       int depth = 1;  // stages per warp
       if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, atoi(e));  // tuning knob
@@ -1097,7 +1118,9 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       f.large_ctas = c->large_ctas;
       const int smem = f.use_smem ? (int)tab_bytes : 0;
       CK(cudaFuncSetAttribute(k3_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      const int grid = (int)std::max<long long>(1, std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * 4));
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_finish, 256, smem));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * std::max(1, occ)));
       k3_finish<<<grid, 256, smem, st>>>(f);
       c->launches++;
       c->last_fused = true;

@@ -142,6 +142,14 @@ __device__ __forceinline__ uint32_t fold_fast(int a, int n) {
   return (f - 1u) < (uint32_t)(n - 1) ? f : 0u;
 }
 
+// predicated reductions without a branch (a divergent branch costs more than the reduction it skips)
+__device__ __forceinline__ void red_shared_inc_if(bool pr, const uint32_t* base, uint32_t idx) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.shared.add.u32 [%1], 1;\n\t}" ::"r"((uint32_t)pr), "r"(smem_u32(base) + idx * 4u) : "memory");
+}
+__device__ __forceinline__ void red_global_inc_if(bool pr, uint32_t* addr) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.global.add.u32 [%1], 1;\n\t}" ::"r"((uint32_t)pr), "l"(addr) : "memory");
+}
+
 // PLAIN = the common configuration, with every per-SNP branch that cannot trigger compiled out: no snp_flags / fix-ups, one
 // background group for all rows (or none), no position restriction of the background, fold on, 4-byte records, no more
 // sample columns than the declared panel (so no count can leave the spectrum), 32 <= n <= 1023 (the privatised corner is
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
             if ((e >> KEY_SHIFT) == key) { c = atomicAdd(tab + h, 1u) & F10; break; }
             h = (h + 1) & (HASH_SLOTS - 1);
           }
-          if (c) w2 += __ldg(q.dxI + c);
+          w2 += __ldg(q.dxI + c);  // dx[0] = 0: no branch for the (common) first SNP of a bin
           nn += 1u;
           aux += c == 0;
         }
@@ -362,12 +370,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
               fa = fold_fast(alt1, p.n1);
               fb = fold_fast(alt2, p.n2);
               if (cta_group >= 0) {  // background: privatised 64 x 64 corner and 1D bins, the rest straight to global memory
-                if (key) {
-                  if ((k1 | k2) < CORNER) atomicAdd(sm.corner + (k1 << 6 | k2), 1u);
-                  else atomicAdd(p.hist + key, 1u);
-                }
-                if (alt1) atomicAdd(sm.h1a + alt1, 1u);
-                if (alt2) atomicAdd(sm.h1b + alt2, 1u);
+                const bool inc = (k1 | k2) < CORNER;
+                red_shared_inc_if(key != 0 && inc, sm.corner, (uint32_t)(k1 << 6 | k2) & (CORNER * CORNER - 1));
+                red_global_inc_if(key != 0 && !inc, p.hist + key);
+                red_shared_inc_if(alt1 != 0, sm.h1a, (uint32_t)alt1);
+                red_shared_inc_if(alt2 != 0, sm.h1b, (uint32_t)alt2);
               }
             } else {
               const uint2 ka = sink_row(p, s, ref1, alt1, ref2, alt2, cta_group, sm, cc);
@@ -475,7 +482,7 @@ __device__ __forceinline__ double exact_bins(const ScoreParams& p, int lo, int c
   return warp_sum(acc);
 }
 
-__global__ void __launch_bounds__(256) k3_finish(const __grid_constant__ FinishParams q) {
+__global__ void __launch_bounds__(256, 4) k3_finish(const __grid_constant__ FinishParams q) {
   // ln b of group 0 staged per CTA: [cr * cr] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
   // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
   // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch

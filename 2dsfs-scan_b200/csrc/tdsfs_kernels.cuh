@@ -19,7 +19,7 @@ namespace tdsfs {
 
 // ------------------------------------------------------------------------------------------------ constants
 constexpr int BLK = 32;               // SNPs per block of the block-transposed genotype layout ("B32")
-constexpr int K1_CWARPS = 16;         // most warps the genotype count kernel can run (each runs its own TMA ring)
+constexpr int K1_CWARPS = 24;         // most warps the genotype count kernel can run (each runs its own TMA ring)
 constexpr int K1_THREADS = K1_CWARPS * 32;  // launch bound; the launch uses cwarps * 32 threads
 constexpr int K1_DEFAULT_WARPS = 12;
 constexpr int K1_ROWS = 128;          // row granularity of host-side upload chunks (multiple of BLK)
@@ -781,23 +781,20 @@ struct FinParams {
 
 __device__ __forceinline__ double ln_count(unsigned long long v) { return v ? log((double)v) : -INFINITY; }
 
-__global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__ FinParams p) {
+// ln tables and interior totals of background group g, by CTA `cta` of `ncta` (all of them must call: the last one to
+// arrive turns the totals into B and ln B)
+__device__ __forceinline__ void finalize_group(const FinParams& p, int g, int cta, int ncta, int ctas_total) {
   __shared__ int s_last;
-  if (p.wait_n) {
-    if ((int)threadIdx.x < p.wait_n) peer_wait(p.wait_flags + threadIdx.x, p.wait_epoch, p.err, p.timeout_cycles);
-    __syncthreads();
-  }
-  const int g = blockIdx.y;
   const uint32_t* h = p.hist + (long long)g * p.gstride;
   unsigned long long local = 0;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < p.bins2d; k += (long long)gridDim.x * blockDim.x) {
+  for (long long k = (long long)cta * blockDim.x + threadIdx.x; k < p.bins2d; k += (long long)ncta * blockDim.x) {
     const uint32_t v = h[k];
     p.lb2[(long long)g * p.bins2d + k] = ln_count(v);
     if (k > 0 && k < p.bins2d - 1) local += v;
   }
   for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.Bsum + g * 3, local);
-  if (blockIdx.x == 0) {
+  if (cta == 0) {
     for (int pop = 0; pop < 2; ++pop) {
       const int n = pop ? p.n2 : p.n1;
       const uint32_t* raw = h + p.bins2d + (pop ? p.R1 : 0);
@@ -817,7 +814,7 @@ __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__
   __threadfence();
   __syncthreads();
   unsigned int* ticket = reinterpret_cast<unsigned int*>(p.Bsum + (long long)p.NG * 3);
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)ctas_total - 1;
   __syncthreads();
   if (s_last) {
     __threadfence();
@@ -827,6 +824,82 @@ __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__
       p.B[(i / 3) * 6 + 3 + i % 3] = b > 0.0 ? log(b) : -INFINITY;
     }
     if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__ FinParams p) {
+  if (p.wait_n) {
+    if ((int)threadIdx.x < p.wait_n) peer_wait(p.wait_flags + threadIdx.x, p.wait_epoch, p.err, p.timeout_cycles);
+    __syncthreads();
+  }
+  finalize_group(p, blockIdx.y, blockIdx.x, gridDim.x, gridDim.x * gridDim.y);
+}
+
+// Multi-GPU, ONE launch per rank between the count kernel and the finish kernel: [barrier: every rank's count kernel is
+// done] -> pull slice `rank` of every rank's histogram over NVLink, sum, push the sum into every rank's histogram ->
+// [barrier: every rank's pushes have landed] -> ln tables and totals of the (now complete) local histogram.  The epoch of
+// the flag barriers lives in device memory (words[0] of `epoch_mem`, advanced by 2 by the last CTA) so that the launch can be
+// replayed unchanged.  Grid <= number of SMs: every CTA is resident while it spins on the flags.
+struct PeerFinParams {
+  PeerParams x;
+  FinParams f;
+  unsigned long long* epoch_mem;  // [0] = last epoch used on this rank
+};
+
+__global__ void __launch_bounds__(256) k_peer_reduce_finalize(const __grid_constant__ PeerFinParams q) {
+  const PeerParams& p = q.x;
+  __shared__ int s_last2;
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(q.epoch_mem) + 1;
+  if ((int)threadIdx.x < p.world) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(p.flags[threadIdx.x] + p.rank, e);
+    }
+    peer_wait(p.flags[p.rank] + threadIdx.x, e, p.err, p.timeout_cycles);
+  }
+  __syncthreads();
+  const long long n4 = p.words / 4;
+  const long long lo = n4 * p.rank / p.world, hi = n4 * (p.rank + 1) / p.world;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < p.world) v[r] = __ldcg(reinterpret_cast<const uint4*>(p.hist[r]) + i);
+    uint4 s = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < p.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    for (int r = 8; r < p.world; ++r) {
+      const uint4 t = __ldcg(reinterpret_cast<const uint4*>(p.hist[r]) + i);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    for (int r = 0; r < p.world; ++r) __stcg(reinterpret_cast<uint4*>(p.hist[r]) + i, s);
+  }
+  if (p.rank == p.world - 1 && blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long w = n4 * 4; w < p.words; ++w) {
+      uint32_t s = 0;
+      for (int r = 0; r < p.world; ++r) s += __ldcg(p.hist[r] + w);
+      for (int r = 0; r < p.world; ++r) __stcg(p.hist[r] + w, s);
+    }
+  // every thread's pushes are ordered before the CTA's ticket; the last CTA tells every rank that this rank is done
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last2 = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last2 && (int)threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + p.rank, e + 1);
+  }
+  // second barrier: every rank's slice has landed in this rank's histogram
+  if ((int)threadIdx.x < p.world) peer_wait(p.flags[p.rank] + threadIdx.x, e + 1, p.err, p.timeout_cycles);
+  __syncthreads();
+  finalize_group(q.f, 0, blockIdx.x, gridDim.x, gridDim.x);
+  // the finalize ticket has seen every CTA: all of them read the epoch long ago.  One thread advances it and resets the
+  // reduce ticket for the next launch (the CTA that does it is the last one through finalize_group's ticket or any
+  // other: the writes only have to happen after every CTA's arrival at the first ticket, which the second barrier implies)
+  if (s_last2 && threadIdx.x == 0) {
+    *p.ticket = 0;
+    *q.epoch_mem = e + 1;
   }
 }
 

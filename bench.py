@@ -230,37 +230,85 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ verification
+_MIX = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5, 0x85EBCA77C2B2AE63,
+                 0xD6E8FEB86659FD93], dtype=np.uint64)
+
+
+def result_checksums(res, chrom_global, empty_bit, none_bits):
+    """Order-independent integer checksums of a rank's windows (identical for every sharding of the same workload):
+    sum over non-empty windows of a 64-bit mix of (chromosome, start, snp_count, n2d, n1d_p1, n1d_p2), and of the statistics
+    rounded to 1e-3 (the fp64 sums of a window run in a lane order that depends on the shard's row offset)."""
+    live = (res["flags"] & empty_bit) == 0
+    with np.errstate(over="ignore"):
+        f = [chrom_global[live].astype(np.uint64), res["start"][live].astype(np.uint64), res["snp_count"][live].astype(np.uint64),
+             res["n2d"][live].astype(np.uint64), res["n1d_p1"][live].astype(np.uint64), res["n1d_p2"][live].astype(np.uint64)]
+        h = np.zeros(int(live.sum()), dtype=np.uint64)
+        for v, m in zip(f, _MIX):
+            h = (h ^ (v * m)) * np.uint64(0xFF51AFD7ED558CCD)
+            h ^= h >> np.uint64(33)
+        ints = int(h.sum(dtype=np.uint64))
+    out = {"windows": int(live.sum()), "snp_count_sum": int(res["snp_count"][live].sum()), "int_checksum": ints}
+    for name, bit in zip(("T2D", "T1D_p1", "T1D_p2"), none_bits):
+        ok = live & ((res["flags"] & bit) == 0) & np.isfinite(res[name])
+        out[name + "_milli_sum"] = int(np.floor(res[name][ok] * 1000.0 + 0.5).astype(np.int64).sum())
+        out[name + "_none"] = int((live & ((res["flags"] & bit) != 0)).sum())
+    return out
+
+
+def oracle_window_check(h, T, G, pos_host, off, res, cfg, n_sample, seed):
+    """Seeded sample of this rank's windows re-scored by the CPU oracle (oracle/sfs_oracle.c decode + the oracle's dense
+    spectra and likelihood) against the GPU's (all-reduced) background.  The oracle is the CHECKER here, never measured."""
+    oracle_modules()
+    import sfs_oracle as O
+    import sfs_oracle_c as OC
+    n1, n2, W = cfg["n1"], cfg["n2"], cfg["W"]
+    w1, w2 = words_for(n1), words_for(n2)
+    RW = w1 + w2
+    g2, g1a, g1b = h.get_background(0)
+    b2 = g2.astype(np.int64).ravel()[1:-1]
+    b1a, b1b = O.fold_dense(g1a.astype(np.int64))[1:-1], O.fold_dense(g1b.astype(np.int64))[1:-1]
+    live = np.flatnonzero((res["flags"] & T.F_EMPTY) == 0)
+    rng = np.random.default_rng(seed)
+    ids = rng.choice(live, size=min(n_sample, len(live)), replace=False)
+    worst, bad = 0.0, 0
+    for wid in ids.tolist():
+        c = int(res["chrom"][wid])
+        pc = pos_host[off[c]:off[c + 1]]
+        lo = int(off[c] + np.searchsorted(pc, res["start"][wid], side="left"))
+        hi = int(off[c] + np.searchsorted(pc, res["end"][wid], side="right"))
+        if hi - lo != int(res["snp_count"][wid]):
+            bad += 1
+            continue
+        blk0, blk1 = lo // 32, (hi + 31) // 32
+        words = G[blk0 * RW * 32:blk1 * RW * 32].cpu().numpy().view(np.uint32)
+        cnt = OC.decode(words, (blk1 - blk0) * 32, w1, w2, n1, n2)[lo - blk0 * 32:hi - blk0 * 32]
+        e2, e1, e1b = O.dense_spectra(cnt, n1, n2)
+        for name, x, b, bit in (("T2D", e2.ravel()[1:-1], b2, T.F_T2D_NONE), ("T1D_p1", O.fold_dense(e1)[1:-1], b1a, T.F_T1D_P1_NONE),
+                                ("T1D_p2", O.fold_dense(e1b)[1:-1], b1b, T.F_T1D_P2_NONE)):
+            exp, none = O.clr_dense(x, b)
+            if none != bool(res["flags"][wid] & bit):
+                bad += 1
+            elif not none:
+                err = abs(res[name][wid] - exp) / max(abs(exp), 1.0) if np.isfinite(exp) else (0.0 if res[name][wid] == exp else 1.0)
+                worst = max(worst, float(err))
+    return {"windows_checked": int(len(ids)), "max_rel_err": worst, "mismatches": int(bad), "tolerance": 1e-9,
+            "ok": bool(bad == 0 and worst <= 1e-9)}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 class _DevBuf:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
-def run_b200(args, cfg):
-    import torch
-    import torch.distributed as dist
-    import tdsfs_capi as T
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ.pop("NCCL_DEBUG")  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+def measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, do_e2e, verify_windows):
+    """Synthesise this rank's shard of `cfg` in HBM and measure the scan on it.  Returns a dict of measurements."""
     n1, n2, W = cfg["n1"], cfg["n2"], cfg["W"]
     w1, w2 = words_for(n1), words_for(n2)
     RW = w1 + w2
-
     # ---- this rank's shard: contiguous chromosomes (strong) or a full copy of the workload per rank (weak)
-    if args.scaling == "strong":
-        chroms = shard_chroms(cfg["C"], world, rank)
-    else:
-        chroms = list(range(cfg["C"]))
+    chroms = shard_chroms(cfg["C"], world, rank) if args.scaling == "strong" else list(range(cfg["C"]))
     sizes_all = chrom_sizes(cfg["S"], cfg["C"])
     starts_all = np.concatenate([[0], np.cumsum(sizes_all)])
     pos_list = positions_for(cfg, chroms)
@@ -272,11 +320,6 @@ def run_b200(args, cfg):
         snp0 += rank * cfg["S"]  # different SNPs on every rank
     S_total = cfg["S"] if args.scaling == "strong" else cfg["S"] * world
 
-    h = T.Handle(local_rank)
-    # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    h.set_stream(stream.cuda_stream)
     h.set_panel(n1, n2, True)
     g_words = max((S_local + 31) // 32, 1) * RW * 32  # B32 layout: blocks of 32 SNPs, zero padded
     G = torch.empty((g_words,), dtype=torch.int32, device=dev)
@@ -302,8 +345,9 @@ def run_b200(args, cfg):
             dist.all_reduce(hist_tensor())
 
     def device_step():
-        """K1 (+ all-reduce of the background) + finalize + K2 + K3/K4, all enqueued on one stream, no host sync."""
-        h.plan(W)                  # K2 on a side stream: overlaps K1 and the all-reduce
+        """plan (K2 on a side stream, arms the fused count kernel) + count kernel (+ all-reduce of the background) + finalize
+        + finish kernel, all enqueued on one stream, no host sync."""
+        h.plan(W)
         h.background(T.BG_GENOME)
         if world > 1:
             exchange()
@@ -315,10 +359,7 @@ def run_b200(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     windows = []
-
     # ---- (A) device-resident throughput
     h.load_genotypes(G, S_local, w1, w2, n1, n2, pos_dev, off)
     if world > 1 and args.exchange == "peer":
@@ -326,11 +367,12 @@ def run_b200(args, cfg):
         h.background(T.BG_GENOME)  # allocates the histogram that the peers map
         peer["on"] = peer_setup(h)
     h.set_sync(False)
+    nwarm = max(args.warmup, 3)
     launches0 = h.launch_count()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(nwarm):
         device_step()
     barrier()
-    launches_per_step = (h.launch_count() - launches0) // max(args.warmup, 3)
+    launches_per_step = (h.launch_count() - launches0) // nwarm
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_a0 = time.time()
     ev0.record(stream)
@@ -340,7 +382,8 @@ def run_b200(args, cfg):
     barrier()
     t_a1 = time.time()
     windows.append((t_a0, t_a1))
-    h._check(h._L.tdsfs_check(h._h))
+    h.check()
+    fused, rec_bytes = h.scan_info()
     ms_total = ev0.elapsed_time(ev1)
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -362,7 +405,6 @@ def run_b200(args, cfg):
         h.scan(W, fetch=False)
         kt.append(h.timings())
     windows.append((t_b0, time.time()))
-    k1_ms = float(np.mean([k["k1_count"] for k in kt]))
     kernel_ms = {k: float(np.mean([x[k] for x in kt])) for k in kt[0]}
     n_windows = h.candidates(W)
     nw_t = torch.tensor([n_windows], dtype=torch.int64, device=dev)
@@ -370,14 +412,32 @@ def run_b200(args, cfg):
         dist.all_reduce(nw_t)
     n_windows_total = int(nw_t.item())
 
+    # ---- (V) verification of the results of this very workload (after the timed regions)
+    res = h.fetch_results(n_windows)
+    chrom_global = res["chrom"].astype(np.int64) + (chroms[0] if chroms else 0)
+    ck = result_checksums(res, chrom_global, T.F_EMPTY, (T.F_T2D_NONE, T.F_T1D_P1_NONE, T.F_T1D_P2_NONE))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, ck)
+        tot = {k: sum(p[k] for p in parts) for k in ck}
+        tot["int_checksum"] %= 1 << 64
+        ck = tot
+    verify = dict(ck)
+    verify["snp_count_sum_equals_S"] = bool(ck["snp_count_sum"] == S_total)
+    verify["note"] = ("order-independent checksums over all windows of all ranks: identical for every N on the same workload "
+                      "(strong scaling); statistics rounded to 1e-3 before summing")
+    if rank == 0 and verify_windows > 0:
+        verify["oracle"] = oracle_window_check(h, T, G, pos_host, off, res, cfg, verify_windows, cfg["seed"])
+        verify["oracle"]["what"] = ("rank 0: seeded sample of windows, rows copied back from HBM and re-scored by oracle/ (C decode + dense "
+                                    "spectra + multinomial log-likelihood ratio) against the GPU's all-reduced background")
+
     # ---- (C) end to end through the C ABI with pinned HOST buffers
     e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         G_host = torch.empty((g_words,), dtype=torch.int32, pin_memory=True)
         G_host.copy_(G)
         pos_pin = torch.from_numpy(pos_host).pin_memory()
         torch.cuda.synchronize()
-        cap = n_windows
 
         def e2e_step():
             h.load_genotypes(G_host, S_local, w1, w2, n1, n2, pos_pin, off)
@@ -391,14 +451,11 @@ def run_b200(args, cfg):
             return h.run_bp(T.BG_GENOME, W, fetch=True)
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        for _ in range(1):
-            res = e2e_step()
+        res2 = e2e_step()
         barrier()
         t_c0 = time.time()
-        ev0.record(stream)
         for _ in range(e2e_steps):
-            res = e2e_step()
-        ev1.record(stream)
+            res2 = e2e_step()
         barrier()
         t_c1 = time.time()
         windows.append((t_c0, t_c1))
@@ -406,20 +463,25 @@ def run_b200(args, cfg):
         tw = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        d2h = sum(v.nbytes for v in res.values())
+        d2h = sum(v.nbytes for v in res2.values())
+        same = all(np.array_equal(res2[k], res[k]) if res[k].dtype != np.float64 else
+                   np.allclose(res2[k], res[k], rtol=1e-10, atol=1e-10, equal_nan=True) for k in res)
         e2e = {"value": S_total / float(tw.item()), "unit": "SNPs/s", "h2d_bytes_per_step": int(g_words * 4 + S_local * 4),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tw.item()) * 1e3, "steps": e2e_steps,
                "api": "tdsfs_load_genotypes(host) + tdsfs_run_bp(host results) via ctypes",
+               "results_equal_device_resident_run": bool(same),
                "note": "per-rank bytes; PCIe host->device copy of the 2-bit matrix dominates"}
-    sampler.stop()
     if peer["on"]:
         from tdsfs_dist import peer_teardown
         peer_teardown(h)
+    del G, pos_dev
+    torch.cuda.empty_cache()
+    return dict(value=value, ms_step=ms_step, kernel_ms=kernel_ms, launches_per_step=int(launches_per_step), e2e=e2e, verify=verify,
+                n_windows_total=n_windows_total, S_local=S_local, S_total=S_total, RW=RW, windows=windows, peer=peer["on"],
+                fused=fused, rec_bytes=rec_bytes)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+
+def roofline_record(cfg, m, world, workload):
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -427,39 +489,109 @@ def run_b200(args, cfg):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    geno_bytes = (n1 + n2) / 4.0
-    achieved = S_local * geno_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
+    geno_bytes = (cfg["n1"] + cfg["n2"]) / 4.0
+    k1_ms = m["kernel_ms"]["k1_count"]
+    achieved = m["S_local"] * geno_bytes / (k1_ms * 1e-3) / 1e9
+    traffic, traffic_note = None, "not captured with ncu for this workload / shard size"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get(args.workload)
+        t = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        ent = t.get(workload, {}).get(str(world))
+        if ent:
+            traffic, traffic_note = ent["bytes"], ent["source"]
     except Exception:  # noqa: BLE001
         pass
-    step_bytes = S_local * (geno_bytes + 4.0)
-    roof = {"bound": "hbm", "kernel": "k1_genotypes (count kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": S_local * geno_bytes, "kernel_ms": k1_ms,
-            "whole_step": {"algorithmic_bytes": step_bytes, "ms": ms_step if world == 1 else kernel_ms["pass_total"],
-                           "achieved": step_bytes / ((ms_step if world == 1 else kernel_ms["pass_total"]) * 1e-3) / 1e9},
-            "kernel_ms_all": kernel_ms,
+    step_ms = m["ms_step"] if world == 1 else m["kernel_ms"]["pass_total"]
+    step_bytes = m["S_local"] * (geno_bytes + 4.0)
+    roof = {"bound": "hbm", "kernel": "k1_fused (count kernel: counts, records, background histograms, window sums)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": m["S_local"] * geno_bytes, "kernel_ms": k1_ms,
+            "whole_step": {"algorithmic_bytes": step_bytes, "ms": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9},
+            "kernel_ms_all": m["kernel_ms"],
             "how": "CUDA events recorded by libtdsfs on the launching stream around each kernel, mean of K synchronous steps "
                    "run right after the timed region; K1 bytes = S*(n1+n2)/4 (2-bit calls), whole step adds 4 B/SNP positions"}
     roof["whole_step"]["frac"] = roof["whole_step"]["achieved"] / peak
+    return roof
 
+
+def run_side(cmd, timeout):
+    """A side benchmark in its own process (its JSON lines are parsed; failures are reported, not fatal)."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        out = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+        return out if r.returncode == 0 else {"error": r.stderr[-300:], "lines": out}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def run_b200(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import tdsfs_capi as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        dist.init_process_group("nccl", device_id=dev)
+    h = T.Handle(local_rank)
+    # a real (non-NULL) stream shared by torch (events, NCCL ordering) and libtdsfs
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    m = measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, not args.no_e2e, args.verify_windows)
+    extra = {}
+    if world == 1 and args.workload == "config5" and not args.no_extra:
+        # BASELINE.json configs[3] (the single-GPU HBM-roofline check) in the same driver-visible record
+        cfg4 = dict(WORKLOADS["config4"])
+        m4 = measure_workload(args, cfg4, h, T, torch, dist, dev, stream, 1, 0, False, 0)
+        extra["config4"] = {"workload": cfg4["name"], "value": m4["value"], "unit": "SNPs/s", "ms_per_step": m4["ms_step"],
+                            "steps": args.steps, "windows": m4["n_windows_total"], "gpu_launches_per_step": m4["launches_per_step"],
+                            "roofline": roofline_record(cfg4, m4, 1, "config4"), "verify": m4["verify"],
+                            "target": "BASELINE/SURVEY 8(d) row 4: >= 37.8 G SNPs/s (0.60 of nominal 8 TB/s on the measured-peak basis)"}
+        m["windows"] += m4["windows"]
+    sampler.stop()
+    clocks = sampler.summary(m["windows"])
+    if world == 1 and rank == 0 and args.workload == "config5" and not args.no_extra:
+        # BASELINE.json configs[0..2] (latency-bound, reference-sized): measured in their own processes after the timed regions
+        extra["config3_sims_batch"] = run_side(["tools/bench_sims.py", "--generations", "2", "--replicates", "100", "--oracle-replicates", "2"], 240)
+        extra["config1_2_ecb"] = run_side(["tools/bench_ecb.py"], 240)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n1, n2, W = cfg["n1"], cfg["n2"], cfg["W"]
+    roof = roofline_record(cfg, m, world, args.workload)
     cb = None
     if world == 1 and not args.no_cpu:
         cb, _, _ = cpu_sample_rate(cfg, args.cpu_seconds, 0)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    line = {"metric": "SNPs/sec, 2D-SFS + T2D/T1D 20 kb window scan", "value": value, "unit": "SNPs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+    line = {"metric": "SNPs/sec, 2D-SFS + T2D/T1D 20 kb window scan", "value": m["value"], "unit": "SNPs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 popcount/histograms + f64 likelihoods", "data": "synthetic",
-            "config": {"workload": cfg["name"], "S": S_total, "n1": n1, "n2": n2, "window_bp": W, "windows": n_windows_total,
+            "config": {"workload": cfg["name"], "S": m["S_total"], "n1": n1, "n2": n2, "window_bp": W, "windows": m["n_windows_total"],
                        "chromosomes": cfg["C"], "sharding": f"contiguous chromosome ranges over {world} rank(s)", "background": "genome-wide"
-                       + ((", all-reduced in place by the library's peer-memory kernel (CUDA IPC over NVLink, uint32 sum)" if peer["on"]
-                          else ", all-reduced (NCCL, uint32 sum)") if world > 1 else ""), "row_bytes": RW * 4,
-                       "l2": "inputs (per-rank genotype matrix %.1f GB) larger than L2" % (S_local * RW * 4 / 1e9)},
-            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "gpu_launches_per_step": int(launches_per_step), "clocks": sampler.summary(windows)}
+                       + ((", all-reduced in place by the library's peer-memory kernel (CUDA IPC over NVLink, uint32 sum)" if m["peer"]
+                          else ", all-reduced (NCCL, uint32 sum)") if world > 1 else ""), "row_bytes": m["RW"] * 4,
+                       "scan_path": ("fused: k1_fused (window sums under the count kernel) + k3_finish" if m["fused"] else "table scorer")
+                       + f", {m['rec_bytes']}-byte per-SNP records",
+                       "generator": "device generator of libtdsfs (tdsfs_synth_genotypes): counter-based mix64 hash instead of Philox, "
+                                    "normal approximation of the Balding-Nichols drift instead of a Beta draw (SURVEY 8(d) names Philox + Beta); "
+                                    "same shape, frequency spectrum family, F = 0.05, 2 % missing; positions = cumsum of Geometric(1/50) gaps",
+                       "l2": "inputs (per-rank genotype matrix %.1f GB) larger than L2" % (m["S_local"] * m["RW"] * 4 / 1e9)},
+            "roofline": roof, "cpu_baseline": cb, "e2e": m["e2e"], "verify": m["verify"], "gpu_launches": int(m["launches_per_step"] * args.steps),
+            "gpu_launches_per_step": m["launches_per_step"], "clocks": clocks, "extra": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -480,6 +612,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--snps", type=int, default=0, help="override the SNP count (profiling runs only; not a bench value)")
+    ap.add_argument("--verify-windows", type=int, default=128, help="windows re-scored by the CPU oracle after the timed region")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config3 / ECB sub-records of the default N=1 run")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
     if args.snps:
