@@ -40,7 +40,7 @@ static int fail(int code, const char* fmt, ...) {
     if (r__) return r__;       \
   } while (0)
 
-enum { EV_BG0, EV_K1, EV_FIN0, EV_FIN1, EV_SC0, EV_K2, EV_K3S, EV_K3L, NEV };
+enum { EV_BG0, EV_K1, EV_FIN0, EV_FIN1, EV_SC0, EV_K2, EV_K3S, EV_K3L, EV_X0, EV_X1, NEV };
 
 struct Chunk {
   long long r0, r1;
@@ -101,6 +101,8 @@ struct tdsfs_ctx {
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
   bool float_bg = false, tables_ready = false, fin_timed = false;
+  bool tables_from_exchange = false;  // the merged exchange kernel already built the tables of this background
+  bool x_timed = false;
   int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
   int* d_err = nullptr;
   // peer-memory exchange of the background histogram (tdsfs_peer_*)
@@ -139,7 +141,7 @@ struct tdsfs_ctx {
   bool results_ready = false;
   // instrumentation
   cudaEvent_t ev[NEV] = {};
-  float ms[8] = {};
+  float ms[10] = {};
   long long launches = 0;
 };
 
@@ -531,6 +533,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   c->NG = NG;
   c->bg_mode = mode;
   c->float_bg = false;
+  c->tables_from_exchange = false;
   c->tables_ready = false;
   c->results_ready = false;
   c->per_chrom_scoring = mode == TDSFS_BG_PER_CHROM;
@@ -783,8 +786,8 @@ extern "C" int tdsfs_peer_export(tdsfs_t* c, int32_t rank, int32_t world, void* 
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   peer_unmap(c);
-  if (!c->d_peer_flags) CKR(dev_alloc(&c->d_peer_flags, PEER_MAX + 1));  // flags, then the reduce kernel's CTA counter
-  CK(cudaMemset(c->d_peer_flags, 0, (PEER_MAX + 1) * sizeof(unsigned long long)));
+  if (!c->d_peer_flags) CKR(dev_alloc(&c->d_peer_flags, PEER_MAX + 2));  // flags, the reduce kernel's CTA counter, the epoch
+  CK(cudaMemset(c->d_peer_flags, 0, (PEER_MAX + 2) * sizeof(unsigned long long)));
   c->peer_pending = 0;
   c->peer_epoch = 0;
   c->peer_rank = rank;
@@ -848,13 +851,53 @@ extern "C" int tdsfs_peer_allreduce_background(tdsfs_t* c) {
   p.epoch = c->peer_epoch + 1;
   c->peer_epoch += 2;
   p.ticket = reinterpret_cast<unsigned int*>(c->d_peer_flags + PEER_MAX);
+  p.epoch_mem = c->d_peer_flags + PEER_MAX + 1;
   const long long n4 = p.words / 4 / p.world + 1;
   const int grid = (int)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)c->sm_count));
+  CK(cudaEventRecord(c->ev[EV_X0], st));
   k_peer_reduce<<<grid, 256, 0, st>>>(p);
+  CK(cudaEventRecord(c->ev[EV_X1], st));
+  c->x_timed = true;
   c->launches += 1;
   c->peer_pending = c->peer_epoch;
   CK(cudaGetLastError());
   c->tables_ready = false;
+  return finish(c);
+}
+
+// All-reduce of the background AND the ln tables in one launch (k_peer_reduce_finalize): replaces the pair
+// tdsfs_peer_allreduce_background + tdsfs_finalize_background (a later tdsfs_finalize_background is then a no-op).
+extern "C" int tdsfs_peer_reduce_finalize(tdsfs_t* c) {
+  if (!c || !c->peer_ready) return fail(TDSFS_ERR_STATE, "tdsfs_peer_export / tdsfs_peer_import first");
+  if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
+  if (c->d_hist != c->peer_exported_hist || c->NG != 1 || c->gstride != c->peer_words)
+    return fail(TDSFS_ERR_STATE, "the histogram changed since tdsfs_peer_export (panel or background mode): export again");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CKR(peer_settle(c));
+  CKR(ensure_tables(c, 1));
+  PeerFinParams q;
+  memset(&q, 0, sizeof q);
+  for (int r = 0; r < PEER_MAX; ++r) { q.x.hist[r] = c->peer_hist[r]; q.x.flags[r] = c->peer_flags[r]; }
+  q.x.rank = c->peer_rank; q.x.world = c->peer_world; q.x.words = c->peer_words; q.x.err = c->d_err;
+  q.x.timeout_cycles = PEER_TIMEOUT_CYCLES;
+  q.x.ticket = reinterpret_cast<unsigned int*>(c->d_peer_flags + PEER_MAX);
+  q.epoch_mem = c->d_peer_flags + PEER_MAX + 1;
+  c->peer_epoch += 2;  // host mirror of the device epoch (the split path passes it as an argument)
+  FinParams& f = q.f;
+  f.hist = c->d_hist; f.gstride = c->gstride; f.NG = 1; f.bins2d = c->bins2d; f.R1 = c->R1; f.R2 = c->R2;
+  f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum; f.B = c->d_B;
+  const int grid = (int)std::max(1, std::min(c->sm_count, (c->bins2d + 255) / 256));
+  CK(cudaEventRecord(c->ev[EV_X0], st));
+  k_peer_reduce_finalize<<<grid, 256, 0, st>>>(q);
+  CK(cudaEventRecord(c->ev[EV_X1], st));
+  c->x_timed = true;
+  c->launches += 1;
+  CK(cudaGetLastError());
+  c->tables_ready = true;
+  c->tables_from_exchange = true;
+  c->float_bg = false;
+  c->fin_timed = false;  // no separate finalize launch to time
   return finish(c);
 }
 
@@ -919,6 +962,7 @@ extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double*
 extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
   if (c->float_bg) return 0;  // tables were built by tdsfs_set_background
+  if (c->tables_from_exchange && c->tables_ready) return 0;  // ... or by tdsfs_peer_reduce_finalize
   if (!c->keys_ready || c->bg_mode == TDSFS_BG_NONE) return fail(TDSFS_ERR_STATE, "no integer background to finalize");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
@@ -1311,7 +1355,7 @@ extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
   if (!c || !ms) return fail(TDSFS_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 8; ++i) c->ms[i] = 0.f;
+  for (int i = 0; i < 10; ++i) c->ms[i] = 0.f;
   if (c->keys_ready) cudaEventElapsedTime(&c->ms[0], c->ev[EV_BG0], c->ev[EV_K1]);
   if (c->fin_timed) cudaEventElapsedTime(&c->ms[1], c->ev[EV_FIN0], c->ev[EV_FIN1]);
   if (c->results_ready) {
@@ -1323,8 +1367,9 @@ extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
     if (c->keys_ready) cudaEventElapsedTime(&c->ms[7], c->ev[EV_BG0], c->ev[EV_K3L]);
   }
   c->ms[5] = c->ms[0];
+  if (c->x_timed) cudaEventElapsedTime(&c->ms[8], c->ev[EV_X0], c->ev[EV_X1]);
   cudaGetLastError();
-  for (int i = 0; i < n && i < 8; ++i) ms[i] = c->ms[i];
+  for (int i = 0; i < n && i < 10; ++i) ms[i] = c->ms[i];
   return 0;
 }
 

@@ -482,65 +482,166 @@ __device__ __forceinline__ double exact_bins(const ScoreParams& p, int lo, int c
   return warp_sum(acc);
 }
 
-__global__ void __launch_bounds__(256, 4) k3_finish(const __grid_constant__ FinishParams q) {
-  // ln b of group 0 staged per CTA: [cr * cr] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
+// Statistics of one small window from its background-dependent sums (g2, g1a, g1b: valid on every lane) and the window sums
+// the count kernel left (wsv: lane l holds word l & 3 of the window's four).  Lanes 0..2 finish one statistic each.
+__device__ __forceinline__ void finish_window(const ScoreParams& p, long long id, int lo, int cnt, double g2, double g1a, double g1b,
+                                              double wsv, const double* lb2, const double* lb1a, const double* lb1b, const double* Bg,
+                                              int lane) {
+  const double bits = __shfl_sync(0xffffffffu, wsv, 3);
+  const uint32_t nt = (uint32_t)__double2loint(bits), meta = (uint32_t)__double2hiint(bits);
+  const int Nq = lane == 0 ? (int)(nt & 0x3FF) : (lane == 1 ? (int)((nt >> 10) & 0x3FF) : (int)(nt >> 20));
+  const double Gq = lane == 0 ? g2 : (lane == 1 ? g1a : g1b);
+  const bool one = lane < 3 && (meta & (WS_ONE_2D << lane)) != 0;
+  const bool own = lane < 3 && Nq > 0 && (double)Nq == __ldg(Bg + lane);  // N == B: possibly the background itself
+  double acc = wsv - Gq;
+  const uint32_t exact = __ballot_sync(0xffffffffu, one || own) & 7u;
+  if (exact) {  // per-bin form for the spectra where the reference's difference of logpmfs is exactly 0.0
+    for (int w = 0; w < 3; ++w)
+      if (exact & (1u << w)) {
+        const double a = exact_bins(p, lo, cnt, w, w == 0 ? lb2 : (w == 1 ? lb1a : lb1b), lane);
+        if (lane == w) acc = a;
+      }
+  }
+  bool none = false;
+  double Tq = 0.0;
+  if (lane < 3) Tq = clr_value(p, Nq, acc, Bg, lane, none);
+  const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
+  if (lane == 0) {
+    uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
+    if (p.snp_mode && !(meta & WS_NALL)) f |= TDSFS_F_SKIPPED;  // :1496 window skipped when its 2D spectrum sums to 0
+    p.r_count[id] = (int)(meta & 0x3FF);
+    p.r_flags[id] = f;
+    p.r_T2[id] = Tq;
+    p.r_n2[id] = Nq;
+  } else if (lane == 1) {
+    p.r_T1a[id] = Tq;
+    p.r_n1a[id] = Nq;
+  } else if (lane == 2) {
+    p.r_T1b[id] = Tq;
+    p.r_n1b[id] = Nq;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ FinishParams q) {
+  // ln b of group 0 staged per CTA: [64 x 64] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
   // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
   // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch
   extern __shared__ __align__(16) double sd[];
   const ScoreParams& p = q.s;
   const int lane = threadIdx.x & 31;
   const bool fast = q.use_smem != 0;  // host: narrow records, one background group, spectrum at least 64 x 64
-  double* s_c = sd;
-  double* s_a = sd + CORNER * CORNER;
-  double* s_b = s_a + 2 * p.n1 + 1;
+  const uint32_t last = (uint32_t)p.bins2d - 1;
+  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (fast) {
+    double* s_c = sd;
+    double* s_a = sd + CORNER * CORNER;
+    double* s_b = s_a + 2 * p.n1 + 1;
     for (int i = threadIdx.x; i < CORNER * CORNER; i += blockDim.x) s_c[i] = i ? __ldg(p.lb2 + (long long)(i >> 6) * p.C2 + (i & 63)) : 0.0;
     for (int i = threadIdx.x; i <= 2 * p.n1; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n1); s_a[i] = f ? __ldg(p.lb1a + f) : 0.0; }
     for (int i = threadIdx.x; i <= 2 * p.n2; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n2); s_b[i] = f ? __ldg(p.lb1b + f) : 0.0; }
-  }
-  __syncthreads();
-  const uint32_t last = (uint32_t)p.bins2d - 1;
-  const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
-  const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
-  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); id < p.ncand; id += nwarp) {
-    const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
-    const int cnt = hi - lo;
-    if (cnt == 0 || cnt > WCAP) continue;  // empty: flagged by K2; large: the CTA path below
-    const int g = p.score_group ? __ldg(p.score_group + __ldg(p.wchrom + id)) : 0;
-    const double* lb2 = p.lb2 + (long long)g * p.bins2d;
-    const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
-    const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
-    const double* Bg = p.B + g * 6;
-    double g2 = 0.0, g1a = 0.0, g1b = 0.0;
-    if (fast) {
-      constexpr int Q = 8;  // records per lane in flight
-      const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec) + lo;
-      for (int base = 0; base < cnt; base += Q * 32) {
-        uint32_t r[Q];
-        double l2[Q], la[Q], lb[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-          const int i = base + j * 32 + lane;
-          r[j] = i < cnt ? __ldcs(rec + i) : 0u;  // 0 decodes to the skipped bin: every table holds 0 there
-        }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-          const uint32_t k1 = r[j] & m1, k2 = (r[j] >> sh2) & m2;
-          const uint32_t a1 = k1 + 2u * ((r[j] >> shd1) & md), a2 = k2 + 2u * (r[j] >> shd2);
-          if ((k1 | k2) < (uint32_t)CORNER) {
-            l2[j] = s_c[(k1 << 6) | k2];
-          } else {
-            const uint32_t key = k1 * (uint32_t)p.C2 + k2;
-            l2[j] = key != last ? __ldg(lb2 + key) : 0.0;
-          }
-          la[j] = s_a[a1];
-          lb[j] = s_b[a2];
-        }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+    __syncthreads();
+    // Every warp owns a CONTIGUOUS range of candidate windows, hence a contiguous stream of records: it reads the stream in
+    // batches of 256 records (the next batch is always in flight while the current one is processed) and cuts it into
+    // windows as it goes.
+    const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
+    const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
+    const long long wa = p.ncand * wid / nwarp, wb = p.ncand * (wid + 1) / nwarp;
+    // first valid (non-empty, at most WCAP SNPs) window at or after `from`
+    auto seek = [&](long long from, int& lo, int& hi) -> long long {
+      while (from < wb) {
+        lo = __ldg(p.wlo + from);
+        hi = __ldg(p.whi + from);
+        if (hi > lo && hi - lo <= WCAP) break;
+        ++from;
       }
-    } else {
+      return from;
+    };
+    int lo = 0, hi = 0;
+    long long id = seek(wa, lo, hi);
+    if (id < wb) {
+      const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec);
+      const int s_end = __ldg(p.whi + wb - 1);  // rows of this warp's windows end here (whi is non-decreasing)
+      constexpr int Q = 8;
+      uint32_t rn[Q];
+      int base = lo;  // row of lane 0, sub-row 0 of the batch in `rn`
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const int row = base + j * 32 + lane;
+        rn[j] = row < s_end ? __ldcs(rec + row) : 0u;
+      }
+      double wsv = __ldg(q.ws + id * 4 + (lane & 3));
+      int nlo = 0, nhi = 0;  // the window after the current one, looked up ahead of its use
+      long long nid = seek(id + 1, nlo, nhi);
+      double g2 = 0.0, g1a = 0.0, g1b = 0.0;
+      while (id < wb) {
+        uint32_t r[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) r[j] = rn[j];
+        const int cur = base;
+        base += Q * 32;
+        if (base < s_end) {
+#pragma unroll
+          for (int j = 0; j < Q; ++j) {
+            const int row = base + j * 32 + lane;
+            rn[j] = row < s_end ? __ldcs(rec + row) : 0u;
+          }
+        }
+#pragma unroll
+        for (int h4 = 0; h4 < Q; h4 += 4) {
+          double l2[4], la[4], lb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t rr = r[h4 + j];
+            const uint32_t k1 = rr & m1, k2 = (rr >> sh2) & m2;
+            const uint32_t a1 = k1 + 2u * ((rr >> shd1) & md), a2 = k2 + 2u * (rr >> shd2);
+            if ((k1 | k2) < (uint32_t)CORNER) {
+              l2[j] = s_c[(k1 << 6) | k2];
+            } else {
+              const uint32_t key = k1 * (uint32_t)p.C2 + k2;
+              l2[j] = key != last ? __ldg(p.lb2 + key) : 0.0;
+            }
+            la[j] = s_a[a1];
+            lb[j] = s_b[a2];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rb = cur + (h4 + j) * 32;  // first row of this sub-row
+            const int row = rb + lane;
+            while (id < wb) {
+              if (rb >= lo && rb + 32 <= hi) {  // the whole sub-row lies inside the current window
+                g2 += l2[j]; g1a += la[j]; g1b += lb[j];
+                break;
+              }
+              if (rb + 32 <= lo) break;         // before the current window (rows of a skipped window)
+              const bool in = row >= lo && row < hi;
+              g2 += in ? l2[j] : 0.0; g1a += in ? la[j] : 0.0; g1b += in ? lb[j] : 0.0;
+              if (hi > rb + 32) break;          // the window continues in the next sub-row
+              // the current window ends inside this sub-row: finish it, move to the next one
+              g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
+              finish_window(p, id, lo, hi - lo, g2, g1a, g1b, wsv, p.lb2, p.lb1a, p.lb1b, p.B, lane);
+              g2 = g1a = g1b = 0.0;
+              id = nid; lo = nlo; hi = nhi;
+              if (id < wb) {
+                wsv = __ldg(q.ws + id * 4 + (lane & 3));
+                nid = seek(id + 1, nlo, nhi);
+              }
+            }
+          }
+        }
+        if (cur >= s_end) break;  // a batch past the end only closes a window that ended exactly on the previous batch's last row
+      }
+    }
+  } else {
+    for (long long id = wid; id < p.ncand; id += nwarp) {
+      const int lo = __ldg(p.wlo + id), hi = __ldg(p.whi + id);
+      const int cnt = hi - lo;
+      if (cnt == 0 || cnt > WCAP) continue;  // empty: flagged by K2; large: the CTA path below
+      const int g = p.score_group ? __ldg(p.score_group + __ldg(p.wchrom + id)) : 0;
+      const double* lb2 = p.lb2 + (long long)g * p.bins2d;
+      const double* lb1a = p.lb1a + (long long)g * (p.n1 + 1);
+      const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
+      double g2 = 0.0, g1a = 0.0, g1b = 0.0;
       constexpr int Q = 4;
       for (int base = 0; base < cnt; base += Q * 32) {
         uint2 r[Q];
@@ -560,43 +661,9 @@ __global__ void __launch_bounds__(256, 4) k3_finish(const __grid_constant__ Fini
 #pragma unroll
         for (int j = 0; j < Q; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
       }
-    }
-    g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
-    // window sums of the count kernel: lanes 0..2 take one statistic each
-    const double* wsp = q.ws + id * 4;
-    const double bits = __ldg(wsp + 3);
-    const uint32_t nt = (uint32_t)__double2loint(bits), meta = (uint32_t)__double2hiint(bits);
-    const int Nq = lane == 0 ? (int)(nt & 0x3FF) : (lane == 1 ? (int)((nt >> 10) & 0x3FF) : (int)(nt >> 20));
-    const double Wq = lane < 3 ? __ldg(wsp + lane) : 0.0;
-    const double Gq = lane == 0 ? g2 : (lane == 1 ? g1a : g1b);
-    const bool one = lane < 3 && (meta & (WS_ONE_2D << lane)) != 0;
-    const bool own = lane < 3 && Nq > 0 && (double)Nq == __ldg(Bg + lane);  // N == B: possibly the background itself
-    double acc = Wq - Gq;
-    const uint32_t exact = __ballot_sync(0xffffffffu, one || own) & 7u;
-    if (exact) {  // per-bin form for the spectra where the reference's difference of logpmfs is exactly 0.0
-      for (int w = 0; w < 3; ++w)
-        if (exact & (1u << w)) {
-          const double a = exact_bins(p, lo, cnt, w, w == 0 ? lb2 : (w == 1 ? lb1a : lb1b), lane);
-          if (lane == w) acc = a;
-        }
-    }
-    bool none = false;
-    double Tq = 0.0;
-    if (lane < 3) Tq = clr_value(p, Nq, acc, Bg, lane, none);
-    const uint32_t nb = __ballot_sync(0xffffffffu, none) & 7u;  // bit q = statistic q is None
-    if (lane == 0) {
-      uint8_t f = (uint8_t)nb;  // TDSFS_F_T2D_NONE = 1, _P1_NONE = 2, _P2_NONE = 4
-      if (p.snp_mode && !(meta & WS_NALL)) f |= TDSFS_F_SKIPPED;  // :1496 window skipped when its 2D spectrum sums to 0
-      p.r_count[id] = (int)(meta & 0x3FF);
-      p.r_flags[id] = f;
-      p.r_T2[id] = Tq;
-      p.r_n2[id] = Nq;
-    } else if (lane == 1) {
-      p.r_T1a[id] = Tq;
-      p.r_n1a[id] = Nq;
-    } else if (lane == 2) {
-      p.r_T1b[id] = Tq;
-      p.r_n1b[id] = Nq;
+      g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
+      const double wsv = __ldg(q.ws + id * 4 + (lane & 3));
+      finish_window(p, id, lo, cnt, g2, g1a, g1b, wsv, lb2, lb1a, lb1b, p.B + g * 6, lane);
     }
   }
   // windows above WCAP SNPs (K2's list, complete before this launch): one CTA each over dense scratch

@@ -646,6 +646,7 @@ struct PeerParams {
   int* err;
   long long timeout_cycles;
   unsigned int* ticket;      // CTA arrival counter of k_peer_reduce (reset by its last CTA)
+  unsigned long long* epoch_mem;  // device copy of the last epoch used (read by k_peer_reduce_finalize)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -720,7 +721,10 @@ __global__ void __launch_bounds__(256) k_peer_reduce(const __grid_constant__ Pee
       __threadfence_system();
       st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch + 1);
     }
-    if (threadIdx.x == 0) *p.ticket = 0;
+    if (threadIdx.x == 0) {
+      *p.ticket = 0;
+      *p.epoch_mem = p.epoch + 1;
+    }
   }
 }
 

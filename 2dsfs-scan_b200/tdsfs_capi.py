@@ -20,7 +20,7 @@ EXPORTS = [
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
-    "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_close",
+    "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_reduce_finalize", "tdsfs_peer_close",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_version",
 ]
 
@@ -173,6 +173,10 @@ class Handle:
     def peer_allreduce_background(self):
         self._check(self._L.tdsfs_peer_allreduce_background(self._h))
 
+    def peer_reduce_finalize(self):
+        """All-reduce of the background and the ln tables in one launch (finalize_background afterwards is a no-op)."""
+        self._check(self._L.tdsfs_peer_reduce_finalize(self._h))
+
     def peer_close(self):
         self._check(self._L.tdsfs_peer_close(self._h))
 
@@ -271,9 +275,9 @@ class Handle:
                                                   C.c_double(missing_rate), C.c_double(fst)))
 
     def timings(self):
-        ms = (C.c_float * 8)()
-        self._check(self._L.tdsfs_timings(self._h, ms, C.c_int32(8)))
-        names = ["k1_count", "finalize", "k2_bounds", "k3_small", "k3_large", "background_call", "scan_call", "pass_total"]
+        ms = (C.c_float * 10)()
+        self._check(self._L.tdsfs_timings(self._h, ms, C.c_int32(10)))
+        names = ["k1_count", "finalize", "k2_bounds", "k3_small", "k3_large", "background_call", "scan_call", "pass_total", "exchange"]
         return dict(zip(names, list(ms)))
 
     def launch_count(self):

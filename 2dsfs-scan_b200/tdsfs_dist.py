@@ -274,7 +274,7 @@ def sharded_scan(handle, pieces, pos, size, bg_mode, device, *, snp_mode=False, 
         handle.background(bg_mode)
     if bg_mode in (BG_GENOME, BG_CHROM):
         if peer:
-            handle.peer_allreduce_background()
+            handle.peer_reduce_finalize()  # exchange + ln tables in one launch per rank
         else:
             allreduce_background(background_tensor(handle, device), group)
     elif bg_mode == BG_PER_CHROM and plan is not None:

@@ -340,7 +340,7 @@ def measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, do_
     def exchange():
         """Sum the background histogram over ranks in place: the library's peer-memory kernel, else NCCL."""
         if peer["on"]:
-            h.peer_allreduce_background()
+            h.peer_reduce_finalize()  # exchange + ln tables in one launch; finalize_background below is then a no-op
         else:
             dist.all_reduce(hist_tensor())
 

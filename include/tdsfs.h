@@ -151,6 +151,9 @@ int tdsfs_background_device(tdsfs_t* ctx, void** dev_ptr, int64_t* n_words, int3
 int tdsfs_peer_export(tdsfs_t* ctx, int32_t rank, int32_t world, void* blob);
 int tdsfs_peer_import(tdsfs_t* ctx, const void* blobs);
 int tdsfs_peer_allreduce_background(tdsfs_t* ctx);
+/* The same exchange and tdsfs_finalize_background in ONE launch per rank: barrier, pull / sum / push of this rank's slice,
+ * barrier, then the ln tables of the complete local histogram.  A tdsfs_finalize_background that follows is a no-op. */
+int tdsfs_peer_reduce_finalize(tdsfs_t* ctx);
 int tdsfs_peer_close(tdsfs_t* ctx);
 
 /* Copy one group's integer spectra to the host: sfs2d[(2n1+1)*(2n2+1)] row-major (i,j) = calculate_2d_sfs,
@@ -207,7 +210,7 @@ int tdsfs_synth_genotypes(tdsfs_t* ctx, void* G_dev, int64_t S, int64_t snp0, in
                           int32_t ns1, int32_t ns2, uint64_t seed, double missing_rate, double fst);
 /* CUDA-event times (ms) of the last background / finalize / scan calls (synchronises the stream):
  * [0]=count kernel (K1), [1]=finalize, [2]=boundaries (K2), [3]=score small windows (K3/K4), [4]=score large windows,
- * [5]=background call, [6]=scan call, [7]=K1 start -> last score kernel end. */
+ * [5]=background call, [6]=scan call, [7]=K1 start -> last score kernel end, [8]=peer exchange kernel (n >= 9). */
 int tdsfs_timings(tdsfs_t* ctx, float* ms, int32_t n);
 int64_t tdsfs_launch_count(tdsfs_t* ctx); /* kernels launched by this handle so far */
 /* Which path scored the last scan: *fused = 1 when the fused pair ran (tdsfs_plan_* before tdsfs_background on the

@@ -1,6 +1,6 @@
-"""2-GPU parity: a scan sharded by contiguous chromosome ranges with the background all-reduced (NCCL, and the library's
-own peer-memory kernel) equals the single-GPU scan (integers bit for bit, fp64 to 1e-12).  Skipped on boxes with
-fewer than two GPUs."""
+"""2-GPU parity: scans sharded by make_shard_plan (contiguous row ranges, split inside a chromosome on a window boundary) with
+the background exchanged by NCCL or by the library's own peer-memory kernel equal the single-GPU scans (integers bit for
+bit, fp64 to 1e-10).  Skipped on boxes with fewer than two GPUs (run with `gpurun --gpus 2`)."""
 import os
 import socket
 import sys
@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _panel():
     from tdsfs_pack import pack_codes
     rng = np.random.default_rng(17)
-    n1, n2, sizes = 40, 30, [3000, 5000, 2000, 4000, 3500, 2500]
+    n1, n2, sizes = 40, 30, [3000, 9000, 2000, 2500, 1500, 2000]  # the middle of the genome lies inside chromosome 1
     S = sum(sizes)
     f = np.exp(rng.uniform(np.log(0.005), np.log(0.995), size=S))
 
@@ -37,33 +37,49 @@ def _worker(rank, world, port, out, peer=False):
     import torch
     import torch.distributed as dist
     import tdsfs_capi as T
-    from tdsfs_dist import shard_chromosomes, sharded_scan_bp, peer_setup, peer_teardown
+    from tdsfs_dist import make_shard_plan, local_offsets, sharded_scan, peer_setup, peer_teardown
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     n1, n2, sizes, c1, c2, pos, pack_codes = _panel()
     off = np.concatenate([[0], np.cumsum(sizes)])
-    lo, hi = shard_chromosomes(sizes, world)[rank]
-    a, b = off[lo], off[hi]
-    G, w1, w2 = pack_codes(c1[a:b], c2[a:b])
+    dev = torch.device("cuda", rank)
+    results = {}
     h = T.Handle(rank)
     h.set_panel(n1, n2, True)
-    h.load_genotypes(G, int(b - a), w1, w2, n1, n2, pos[a:b], off[lo:hi + 1] - off[lo])
-    if peer:
-        h.background(T.BG_GENOME)  # the histogram must exist before it can be exported
-        assert peer_setup(h), "CUDA IPC mapping of the peers' histograms failed"
-        for _ in range(3):         # repeated scans: barrier epochs advance, the histogram is re-zeroed every time
-            res = sharded_scan_bp(h, 20000, T.BG_GENOME, torch.device("cuda", rank), chrom_base=lo, peer=True)
-        h._check(h._L.tdsfs_check(h._h))
-        peer_teardown(h)
-    else:
-        res = sharded_scan_bp(h, 20000, T.BG_GENOME, torch.device("cuda", rank), chrom_base=lo)
+    loaded = None
+    for name, size, snp, mode, bgc in CASES:
+        plan = make_shard_plan(pos, off, world, **({"N": size} if snp else {"W": size}))
+        pieces = plan[rank]
+        key = tuple((p.lo, p.hi) for p in pieces)
+        if key != loaded:  # rows of this rank's pieces, each piece one local chromosome (a split chromosome is on both ranks)
+            rows = np.concatenate([np.arange(p.lo, p.hi) for p in pieces]) if pieces else np.zeros(0, np.int64)
+            G, w1, w2 = pack_codes(c1[rows], c2[rows])
+            h.load_genotypes(G, len(rows), w1, w2, n1, n2, pos[rows].astype(np.int32), local_offsets(pieces))
+            loaded = key
+        use_peer = peer and mode in (T.BG_GENOME, T.BG_CHROM)
+        if use_peer:
+            h.background(mode, -1 if mode == T.BG_CHROM else 0)  # the histogram must exist before it can be exported
+            assert peer_setup(h), "CUDA IPC mapping of the peers' histograms failed"
+        for _ in range(3 if use_peer else 1):  # repeated scans: barrier epochs advance, the histogram is re-zeroed every time
+            res = sharded_scan(h, pieces, pos, size, mode, dev, snp_mode=snp, bg_chrom=bgc, plan=plan, rank=rank, peer=use_peer)
+        h.check()
+        if use_peer:
+            peer_teardown(h)
+        results[name] = {k: v.tolist() for k, v in res.items()}
     if rank == 0:
-        out["res"] = {k: v.tolist() for k, v in res.items()}
+        out["res"] = results
     dist.destroy_process_group()
+
+
+# name, window size, fixed-SNP?, background mode (tdsfs_capi constants), GLOBAL background chromosome
+CASES = [("bp_genome", 20000, False, 2, None), ("snp_genome", 300, True, 2, None), ("bp_chrom", 20000, False, 3, 1),
+         ("bp_perchrom", 20000, False, 1, None), ("snp_perchrom", 177, True, 1, None)]
 
 
 @pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer-memory"])
 def test_sharded_scan_equals_single_gpu(peer):
+    """2 GPUs, rows split by make_shard_plan (the 9000-SNP chromosome is split on a window boundary): fixed-bp and fixed-SNP
+    windows, genome-wide / single-chromosome (global index) / per-chromosome backgrounds; gathered == single GPU."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -79,10 +95,15 @@ def test_sharded_scan_equals_single_gpu(peer):
     h = T.Handle(0)
     h.set_panel(n1, n2, True)
     h.load_genotypes(G, len(pos), w1, w2, n1, n2, pos, off)
-    single = h.run_bp(T.BG_GENOME, 20000)
-    multi = {k: np.array(v) for k, v in out["res"].items()}
-    for k, v in single.items():
-        if v.dtype == np.float64:
-            assert np.allclose(multi[k], v, rtol=1e-12, atol=1e-12, equal_nan=True), k
-        else:
-            assert np.array_equal(multi[k], v), k
+    for name, size, snp, mode, bgc in CASES:
+        h.plan(size, snp_mode=snp)
+        h.background(mode, bgc if bgc is not None else 0)
+        h.finalize_background()
+        single = h.scan(size, snp_mode=snp)
+        multi = {k: np.array(v) for k, v in out["res"][name].items()}
+        for k, v in single.items():
+            if v.dtype == np.float64:
+                assert np.allclose(multi[k], v, rtol=1e-10, atol=1e-10, equal_nan=True), (name, k)
+            else:
+                assert np.array_equal(multi[k], v), (name, k)
+    h.close()
