@@ -84,11 +84,29 @@ __device__ __forceinline__ int window_id(const FusedParams& q, int s, int pv, Ch
   return (long long)id < q.ncand ? id : -1;  // unsorted positions must not write out of bounds
 }
 
-// Snap a range boundary `t` (a tile-aligned row) back to the first SNP of the window that contains it, so that no window
-// of at most WCAP SNPs is split between two warps (warp-cooperative: all lanes call, all return the same value).
-// is_start = the returned row starts a window (or lies in none); false when the window began more than WCAP rows earlier
-// (such a window is larger than the warp tables: nobody sums it here, the CTA path scores it).
-__device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_start, int lane) {
+// first row after `t` (within WCAP rows, same chromosome or its end) that starts another window than window k of row t;
+// -1 when the window runs on beyond that (warp-cooperative, fixed-bp windows)
+__device__ __forceinline__ int next_window_start(const FusedParams& q, int t, int k, ChromWin& cw, int lane) {
+  const KeyParams& p = q.k;
+  constexpr int STEP = WCAP / 32;  // 24
+  auto past = [&](int s) -> bool { return s >= cw.hi || window_id(q, s, __ldg(p.pos + s), cw) != k; };
+  const bool o1 = past(t + STEP * (lane + 1));
+  const uint32_t b1 = __ballot_sync(0xffffffffu, o1);
+  if (b1 == 0u) return -1;
+  const int f = __ffs(b1) - 1;  // the start lies in (t + STEP f, t + STEP (f + 1)]
+  const int base = t + STEP * f + 1;
+  const bool o2 = lane < STEP ? past(base + lane) : true;
+  const uint32_t b2 = __ballot_sync(0xffffffffu, o2);
+  return min(base + __ffs(b2) - 1, cw.hi);
+}
+
+// Snap a range boundary `t` (a tile-aligned row) to the nearest window start, so that no window of at most WCAP SNPs is split
+// between two warps (warp-cooperative: all lanes call, all return the same value; monotone in t).  Nearest rather than
+// "back to the start of the window that holds t": the ranges of a small shard are only a few windows long, and their
+// lengths then differ by at most one window instead of two.
+// is_start = the returned row starts a window (or lies in none); false when the window holding t began more than WCAP rows
+// earlier (such a window is larger than the warp tables: nobody sums it here, the CTA path scores it).
+__device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_start, int lane, bool nearest) {
   const KeyParams& p = q.k;
   is_start = true;
   if (t <= 0) return 0;
@@ -104,36 +122,42 @@ __device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_st
       is_start = (t - cw.lo) == j * (int)q.W;
       return t;
     }
-    return cw.lo + j * (int)q.W;
+    const int back = cw.lo + j * (int)q.W, fwd = back + (int)q.W;  // fwd <= cw.hi: window j is a full one
+    return (!nearest || (t - back) <= (fwd - t)) ? back : fwd;
   }
   const int k = window_id(q, t, __ldg(p.pos + t), cw);
   const int lo = max(cw.lo, t - WCAP);
   const int span = t - lo;               // 1 .. WCAP
   const int step = (span + 31) >> 5;     // 1 .. 24
+  int back;
   // round 1: lanes probe lo + lane * step (window ids are monotone in the row: false ... false true ... true, t is true)
   const int s1 = lo + lane * step;
   const bool in1 = s1 < t ? window_id(q, s1, __ldg(p.pos + s1), cw) == k : true;
   const uint32_t b1 = __ballot_sync(0xffffffffu, in1);
-  const int f = __ffs(b1) - 1;           // b1 != 0: the lanes with s1 >= t vote true (31 * step may be < span: then f may be 32 - handled below)
-  if (b1 == 0u || f < 0) {               // every probe lies before the window: it starts in (lo + 31 step, t]
+  const int f = __ffs(b1) - 1;
+  if (b1 == 0u) {                        // every probe lies before the window: it starts in (lo + 31 step, t]
     const int base = lo + 31 * step + 1;
     const int sc = base + lane;
     const bool in2 = sc < t ? window_id(q, sc, __ldg(p.pos + sc), cw) == k : true;
     const uint32_t b2 = __ballot_sync(0xffffffffu, in2);
-    return min(base + __ffs(b2) - 1, t);
+    back = min(base + __ffs(b2) - 1, t);
+  } else if (f == 0) {                   // row lo already belongs to the window
+    if (lo != cw.lo) {                   // ... and it began even earlier: larger than WCAP rows
+      is_start = false;
+      return t;
+    }
+    back = lo;                           // ... because the chromosome starts there
+  } else {                               // round 2: the start lies in (lo + (f-1) step, lo + f step]
+    const int base = lo + (f - 1) * step + 1;
+    const int sc = base + lane;
+    const int top = min(lo + f * step, t);
+    const bool in2 = sc < top ? window_id(q, sc, __ldg(p.pos + sc), cw) == k : true;
+    const uint32_t b2 = __ballot_sync(0xffffffffu, in2);
+    back = min(base + __ffs(b2) - 1, top);
   }
-  if (f == 0) {                          // row lo already belongs to the window
-    if (lo == cw.lo) return lo;          // ... because the chromosome starts there
-    is_start = false;                    // ... or the window began earlier: larger than WCAP rows
-    return t;
-  }
-  // round 2: the start lies in (lo + (f-1) step, lo + f step]
-  const int base = lo + (f - 1) * step + 1;
-  const int sc = base + lane;
-  const int top = min(lo + f * step, t);
-  const bool in2 = sc < top ? window_id(q, sc, __ldg(p.pos + sc), cw) == k : true;
-  const uint32_t b2 = __ballot_sync(0xffffffffu, in2);
-  return min(base + __ffs(b2) - 1, top);
+  if (back == t || !nearest) return back;
+  const int fwd = next_window_start(q, t, k, cw, lane);
+  return (fwd < 0 || (t - back) <= (fwd - t)) ? back : fwd;
 }
 
 // folded bin of a raw alt count, 0 when it does not enter the 1D likelihood (same values as folded_interior, fewer instructions)
@@ -199,9 +223,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
 
   if (warp < p.cwarps) {
     const int j = blockIdx.x * p.cwarps + warp;
-    bool st0, st1;
-    const int slo = snap_row(q, target(j), st0, lane);
-    const int shi = snap_row(q, target(j + 1), st1, lane);
+    // Interior boundaries snap to the nearest window start; the ends of the launch snap BACK (rows past r1 may still be
+    // uploading, and the next launch starts from the same back-snapped row), and everything stays between them.
+    bool st0 = true, st1 = true, stl = true, sth = true;
+    const int lo_clamp = r0 > 0 ? snap_row(q, r0, stl, lane, false) : 0;
+    const int hi_clamp = r1 < S ? snap_row(q, r1, sth, lane, false) : S;
+    int slo = lo_clamp, shi = hi_clamp;
+    if (j > 0) {
+      slo = snap_row(q, target(j), st0, lane, true);
+      if (slo <= lo_clamp) { slo = lo_clamp; st0 = stl; }
+      if (slo >= hi_clamp) { slo = hi_clamp; st0 = sth; }
+    } else {
+      st0 = stl;
+    }
+    if (j + 1 < nparts) {
+      shi = snap_row(q, target(j + 1), st1, lane, true);
+      if (shi <= lo_clamp) shi = lo_clamp;
+      if (shi >= hi_clamp) shi = hi_clamp;
+    }
     if (slo < shi) {
       uint8_t* stages = smem + (size_t)warp * depth * stage_stride;
       uint64_t* bars = full + warp * depth;
