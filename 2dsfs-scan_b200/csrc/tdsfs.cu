@@ -101,6 +101,8 @@ struct tdsfs_ctx {
   unsigned long long* d_Bsum = nullptr;
   int table_groups = 0;
   bool float_bg = false, tables_ready = false, fin_timed = false;
+  bool poisson_bg = false;            // the tables hold ln q of a normalised background (tdsfs_set_poisson_background)
+  double pq_n = 0, pq_sum = 0, pq_lnsum = 0;
   bool tables_from_exchange = false;  // the merged exchange kernel already built the tables of this background
   bool x_timed = false;
   int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
@@ -533,6 +535,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   c->NG = NG;
   c->bg_mode = mode;
   c->float_bg = false;
+  c->poisson_bg = false;
   c->tables_from_exchange = false;
   c->tables_ready = false;
   c->results_ready = false;
@@ -953,6 +956,37 @@ extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double*
   CK(cudaStreamSynchronize(st));
   cudaFree(t2); cudaFree(t1a); cudaFree(t1b);
   c->float_bg = true;
+  c->poisson_bg = false;
+  c->per_chrom_scoring = false;
+  c->tables_ready = true;
+  c->results_ready = false;
+  return 0;
+}
+
+extern "C" int tdsfs_set_poisson_background(tdsfs_t* c, const double* q2d) {
+  if (!c || !q2d) return fail(TDSFS_ERR_ARG, "NULL argument");
+  if (!c->bins2d) return fail(TDSFS_ERR_STATE, "tdsfs_set_panel first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CKR(ensure_tables(c, 1));
+  std::vector<double> lq((size_t)c->bins2d);
+  double n = 0, sum = 0, lnsum = 0;
+  for (int k = 0; k < c->bins2d; ++k) {
+    const double q = q2d[k];
+    if (q != 0.0) {  // a bin with a zero expectation is skipped by the score (twoDSFS.py:364)
+      n += 1; sum += q; lnsum += log(q);
+      lq[k] = log(q);
+    } else {
+      lq[k] = -INFINITY;
+    }
+  }
+  CK(cudaMemcpyAsync(c->d_lb2, lq.data(), (size_t)c->bins2d * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(c->d_lb1a, 0, (size_t)(c->n1 + 1) * 8, st));
+  CK(cudaMemsetAsync(c->d_lb1b, 0, (size_t)(c->n2 + 1) * 8, st));
+  CK(cudaStreamSynchronize(st));
+  c->pq_n = n; c->pq_sum = sum; c->pq_lnsum = lnsum;
+  c->float_bg = true;
+  c->poisson_bg = true;
   c->per_chrom_scoring = false;
   c->tables_ready = true;
   c->results_ready = false;
@@ -1116,8 +1150,10 @@ static int plan(tdsfs_ctx* c, long long W, bool snp_mode) {
 extern "C" int tdsfs_plan_bp(tdsfs_t* c, int64_t W) { return plan(c, W, false); }
 extern "C" int tdsfs_plan_snp(tdsfs_t* c, int64_t N) { return plan(c, N, true); }
 
-static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, int64_t cap, int64_t* n_windows) {
+static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, int64_t cap, int64_t* n_windows, bool poisson = false) {
   if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
+  if (poisson != c->poisson_bg) return fail(TDSFS_ERR_STATE, poisson ? "tdsfs_set_poisson_background first" : "the tables hold a Poisson background: tdsfs_scan_poisson_bp, or set a likelihood background");
+  if (poisson && c->fold) return fail(TDSFS_ERR_STATE, "the Poisson score works on the unfolded spectrum: tdsfs_set_panel(..., fold = 0)");
   if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
   if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
   CK(cudaSetDevice(c->device));
@@ -1142,6 +1178,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     s.r_count = c->r_count; s.r_n2 = c->r_n2; s.r_n1a = c->r_n1a; s.r_n1b = c->r_n1b; s.r_T2 = c->r_T2; s.r_T1a = c->r_T1a;
     s.r_T1b = c->r_T1b; s.r_flags = c->r_flags; s.large = c->d_large; s.nlarge = c->d_nlarge;
     s.fmt = c->fmt; s.C2 = c->R2;
+    s.poisson = poisson ? 1 : 0; s.pq_n = c->pq_n; s.pq_sum = c->pq_sum; s.pq_lnsum = c->pq_lnsum;
     const long long sstride = (long long)c->bins2d + c->n1 + 1 + c->n2 + 1;
     if (!c->d_scratch) {  // dense scratch of the large-window path, one slab per CTA
       c->large_ctas = (int)std::max<long long>(8, std::min<long long>(2 * c->sm_count, (256LL << 20) / (sstride * 4)));
@@ -1150,7 +1187,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
     }
     s.scratch = c->d_scratch;
     const int gwords = score_group_smem_words(c->n1, c->n2);
-    if (c->ws_ready && c->fused_W == W && c->fused_snp == (int)snp_mode) {
+    if (c->ws_ready && c->fused_W == W && c->fused_snp == (int)snp_mode && !poisson) {
       // fused scan: the count kernel left every small window's background-independent sums; one launch gathers ln b over
       // the records, finishes the statistics and scores the large windows
       FinishParams f;
@@ -1181,9 +1218,10 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       int G = c->score_group_warps;
       if (ncand < 16LL * c->sm_count * 24) G = std::max(G, 2);
       if (const char* e = getenv("TDSFS_SCORE_G")) G = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);  // tuning knob
+      if (poisson) G = 1;
       while (G < SCORE_WARPS && (SCORE_WARPS / G) * gwords * 4 > 200 * 1024) G *= 2;  // fewer, wider groups for big panels
       const int smem = (SCORE_WARPS / G) * gwords * 4;
-      const bool extra = snp_mode || c->dFlags != nullptr;
+      const bool extra = snp_mode || c->dFlags != nullptr || poisson;
 #define TDSFS_PICK(K, E) (G >= 8 ? K<8, E> : (G == 4 ? K<4, E> : (G == 2 ? K<2, E> : K<1, E>)))
       void (*sk)(ScoreParams) = extra ? TDSFS_PICK(k3_score_small, true) : TDSFS_PICK(k3_score_small, false);
 #undef TDSFS_PICK
@@ -1227,6 +1265,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
 
 extern "C" int tdsfs_scan_bp(tdsfs_t* c, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, W, false, out, cap, n); }
 extern "C" int tdsfs_scan_snp(tdsfs_t* c, int64_t N, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, N, true, out, cap, n); }
+extern "C" int tdsfs_scan_poisson_bp(tdsfs_t* c, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n) { return scan(c, W, false, out, cap, n, true); }
 
 // Synchronise and surface deferred device-side errors (range check of the count kernel).
 extern "C" int tdsfs_check(tdsfs_t* c) {

@@ -995,6 +995,10 @@ struct ScoreParams {
   const void* rec;       // per-SNP records (RecFmt)
   RecFmt fmt;
   int C2;                // 2 n2 + 1
+  // legacy Poisson composite score (reference scripts/twoDSFS.py:336-463) instead of the likelihood ratios: lb2 holds ln q of
+  // the normalised background (-inf where q = 0), the spectrum is unfolded and every bin but (0,0) counts
+  int poisson;
+  double pq_n, pq_sum, pq_lnsum;  // number of bins with q != 0, their sum, the sum of their logarithms
   const uint8_t* flags;
   const int32_t* wlo;
   const int32_t* whi;
@@ -1119,7 +1123,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
   for (int i = tg; i < HASH_SLOTS; i += GT) tab[i] = EMPTY_KEY;
   for (int i = tg; i < nw1 + nw2; i += GT) h1a[i] = 0;
   gsync();
-  const uint32_t last = (uint32_t)p.bins2d - 1;
+  const uint32_t last = p.poisson ? 0xFFFFFFFFu : (uint32_t)p.bins2d - 1;
   const bool has_flags = EXTRA && p.flags != nullptr;
   const bool snp_mode = EXTRA && p.snp_mode;
 
@@ -1190,7 +1194,26 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
     // come from L2 (~700 cycles), so their number in flight - not their count - sets the time of this pass.
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
     uint32_t N2 = 0, N1a = 0, N1b = 0;
-    {
+    double pz_lg0 = 0.0, pz_lg1 = 0.0;  // Poisson score: sum of lgamma(x + 1) and of lgamma(x + 2) over the bins with q != 0
+    uint32_t pz_xq = 0;                 // ... and the number of SNPs in those bins
+    if (EXTRA && p.poisson) {
+      // the table walk of the Poisson score: x ln q - lgamma(x + 1) over the populated bins with a non-zero expectation
+      for (int j0 = tg; j0 < HASH_SLOTS; j0 += GT) {
+        const uint32_t e = tab[j0];
+        if (e != EMPTY_KEY) {
+          tab[j0] = EMPTY_KEY;
+          const uint32_t x = e & ((1u << KEY_SHIFT) - 1);
+          const double lq = __ldg(lb2 + (e >> KEY_SHIFT));
+          N2 += x;
+          if (lq != -INFINITY) {  // a zero expectation is skipped (:364)
+            a2 = fma(u32_to_double(x), lq, a2);
+            pz_lg0 += lgamma((double)x + 1.0);
+            pz_lg1 += lgamma((double)x + 2.0);
+            pz_xq += x;
+          }
+        }
+      }
+    } else {
       constexpr int PER = HASH_SLOTS / GT;       // slots per thread
       constexpr int U = PER < 8 ? PER : 8;
 #pragma unroll 1
@@ -1272,6 +1295,28 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32) k3_score_small(const __grid_
         }
       }
     }
+    if (EXTRA && p.poisson) {
+      // sum over the bins with q != 0 of poisson.logpmf(int(x + 1/total), S_w q), S_w = total + bins / total (:295-303, :346-371):
+      // (e nQ + X_Q) ln S_w + e sum ln q + sum x ln q - S_w sum q - sum lgamma(x + e + 1), e = 1 only when total == 1
+      pz_lg0 = warp_sum(pz_lg0); pz_lg1 = warp_sum(pz_lg1);
+      pz_xq = __reduce_add_sync(0xffffffffu, pz_xq);
+      // (the host launches the Poisson scan with one warp per window: nothing to combine across warps)
+      if (wg == 0 && lane == 0) {
+        if (!has_flags) count = cnt;
+        const int total = (int)(nn & 0x3FF);
+        double P = 0.0;
+        if (total > 0) {
+          const double Sw = (double)total + (double)p.bins2d / (double)total;
+          const double e = total == 1 ? 1.0 : 0.0;
+          P = (e * p.pq_n + (double)pz_xq) * log(Sw) + e * p.pq_lnsum + a2 - Sw * p.pq_sum - (total == 1 ? pz_lg1 : pz_lg0);
+        }
+        p.r_count[id] = count;
+        p.r_flags[id] = 0;
+        p.r_T2[id] = P;
+        p.r_n2[id] = total;
+        p.r_T1a[id] = 0.0; p.r_T1b[id] = 0.0; p.r_n1a[id] = 0; p.r_n1b[id] = 0;
+      }
+    } else
     if (wg == 0) {  // lanes 0..2 finish one statistic each (ln N from the multiplicity table, ln B precomputed)
       if (!has_flags) count = cnt;
       const int Nq = lane == 0 ? (int)(nn & 0x3FF) : (lane == 1 ? (int)((nn >> 10) & 0x3FF) : (int)(nn >> 20));
@@ -1311,7 +1356,7 @@ __device__ __forceinline__ void score_large_windows(const ScoreParams& p, int ct
   uint32_t* h2 = p.scratch + (long long)cta * sstride;
   uint32_t* h1a = h2 + p.bins2d;
   uint32_t* h1b = h1a + p.n1 + 1;
-  const uint32_t last = (uint32_t)p.bins2d - 1;
+  const uint32_t last = p.poisson ? 0xFFFFFFFFu : (uint32_t)p.bins2d - 1;
   for (int w = cta; w < nl; w += ncta) {
     const long long id = p.large[w];
     const int lo = p.wlo[id], hi = p.whi[id];
@@ -1321,6 +1366,8 @@ __device__ __forceinline__ void score_large_windows(const ScoreParams& p, int ct
     const double* lb1b = p.lb1b + (long long)g * (p.n2 + 1);
     int N2 = 0, N1a = 0, N1b = 0, nall = 0, count = 0;
     double a2 = 0.0, a1a = 0.0, a1b = 0.0;
+    double pz_lg = 0.0;  // Poisson score: lgamma term (a window above WCAP SNPs has total > 1)
+    int pz_xq = 0;
     for (int s = lo + tid; s < hi; s += LARGE_THREADS) {
       const uint2 r = load_rec(p.rec, p.fmt, s, p.n1, p.n2, p.C2);
       const uint32_t k = r.x, a = r.y;
@@ -1338,7 +1385,9 @@ __device__ __forceinline__ void score_large_windows(const ScoreParams& p, int ct
       const uint32_t k = r.x, a = r.y;
       if (k != 0 && k != last) {
         const uint32_t x = atomicExch(h2 + k, 0u);
-        if (x) a2 = fma((double)x, ln_mult(p, x) - lb2[k], a2);
+        if (x && p.poisson) {
+          if (lb2[k] != -INFINITY) { a2 = fma((double)x, lb2[k], a2); pz_lg += lgamma((double)x + 1.0); pz_xq += (int)x; }
+        } else if (x) a2 = fma((double)x, ln_mult(p, x) - lb2[k], a2);
       }
       const int fa = (int)(a & 0xFFFF), fb = (int)(a >> 16);
       if (fa) {
@@ -1351,6 +1400,7 @@ __device__ __forceinline__ void score_large_windows(const ScoreParams& p, int ct
       }
     }
     // block reduce
+    if (p.poisson) { a1a = pz_lg; N1a = pz_xq; }  // reduced in the slots of the (unused) 1D statistics
     double dv[3] = {a2, a1a, a1b};
     int iv[5] = {N2, N1a, N1b, nall, count};
     for (int q = 0; q < 3; ++q) { dv[q] = warp_sum(dv[q]); if (lane == 0) red_d[q][warp] = dv[q]; }
@@ -1359,7 +1409,17 @@ __device__ __forceinline__ void score_large_windows(const ScoreParams& p, int ct
     if (tid == 0) {
       for (int q = 0; q < 3; ++q) { double t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_d[q][x]; dv[q] = t; }
       for (int q = 0; q < 5; ++q) { int t = 0; for (int x = 0; x < LARGE_THREADS / 32; ++x) t += red_i[q][x]; iv[q] = t; }
-      write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[0], dv[1], dv[2], p.B + g * 6);
+      if (p.poisson) {
+        const int total = iv[0];
+        const double Sw = (double)total + (double)p.bins2d / (double)total;
+        p.r_count[id] = iv[4];
+        p.r_flags[id] = 0;
+        p.r_T2[id] = (double)iv[1] * log(Sw) + dv[0] - Sw * p.pq_sum - dv[1];
+        p.r_n2[id] = total;
+        p.r_T1a[id] = 0.0; p.r_T1b[id] = 0.0; p.r_n1a[id] = 0; p.r_n1b[id] = 0;
+      } else {
+        write_result(p, id, iv[4], iv[3], iv[0], iv[1], iv[2], dv[0], dv[1], dv[2], p.B + g * 6);
+      }
     }
     __syncthreads();
   }

@@ -19,7 +19,7 @@ EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
-    "tdsfs_scan_snp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
+    "tdsfs_scan_snp", "tdsfs_set_poisson_background", "tdsfs_scan_poisson_bp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_reduce_finalize", "tdsfs_peer_close",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_version",
 ]
@@ -195,6 +195,21 @@ class Handle:
         b1b = np.ascontiguousarray(b1b, dtype=np.float64)
         assert b2d.size == R1 * R2 and b1a.size == self.n1 + 1 and b1b.size == self.n2 + 1
         self._check(self._L.tdsfs_set_background(self._h, _ptr(b2d), _ptr(b1a), _ptr(b1b)))
+
+    def set_poisson_background(self, q2d):
+        """Normalised 2D background of the legacy Poisson score (dense (2n1+1) x (2n2+1), unfolded)."""
+        R1, R2 = 2 * self.n1 + 1, 2 * self.n2 + 1
+        q2d = np.ascontiguousarray(q2d, dtype=np.float64).reshape(-1)
+        assert q2d.size == R1 * R2
+        self._check(self._L.tdsfs_set_poisson_background(self._h, _ptr(q2d)))
+
+    def scan_poisson(self, window_bp):
+        """Poisson composite score of every fixed-bp window: dict of arrays, T2D = the score."""
+        cap = self.candidates(window_bp, False)
+        arrs, r = self._alloc_result(cap)
+        n = C.c_int64()
+        self._check(self._L.tdsfs_scan_poisson_bp(self._h, C.c_int64(window_bp), C.byref(r), C.c_int64(cap), C.byref(n)))
+        return {k: v[:n.value] for k, v in arrs.items()}
 
     def finalize_background(self):
         self._check(self._L.tdsfs_finalize_background(self._h))

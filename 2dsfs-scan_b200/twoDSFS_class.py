@@ -107,10 +107,30 @@ class LikelihoodInference_jointSFS:
                 raise TypeError(f"this PackedPanel holds populations {data_dict.pops}; {(pop1, pop2)} requested (use a data_dict)")
             return data_dict
         n = len(data_dict)
-        tag = (id(data_dict), n, pop1, pop2, next(iter(data_dict)) if n else None, next(reversed(data_dict)) if n else None)
+        tag = (id(data_dict), n, pop1, pop2, self._fingerprint(data_dict, n, pop1, pop2))
         if self._tcache is None or self._tcache[0] != tag:
             self._tcache = (tag, SnpTable.from_dict(data_dict, pop1, pop2))
         return self._tcache[1]
+
+    @staticmethod
+    def _fingerprint(data_dict, n, pop1, pop2, samples=512):
+        """Content fingerprint of the array-form cache: first / last key and the (key, calls, annotation) of up to `samples`
+        evenly spaced records.  The reference re-reads the dict on every call; the cache only skips the dict -> array
+        conversion when the same dict object is scanned again.  An in-place edit of a record that is not sampled is NOT seen:
+        call invalidate_cache() after mutating a data_dict between scans (or pass a new dict)."""
+        if n == 0:
+            return ()
+        import itertools
+        step = max(1, n // samples)
+        out = [next(iter(data_dict)), next(reversed(data_dict))]
+        for k, v in itertools.islice(data_dict.items(), 0, None, step):
+            c = v.get("calls", {})
+            out.append((k, c.get(pop1), c.get(pop2), v.get("annotation")))
+        return hash(tuple(out))
+
+    def invalidate_cache(self):
+        """Forget the cached array form of the last data_dict (after editing a dict in place between scans)."""
+        self._tcache = None
 
     def _int_filters(self):
         # calculate_2d_sfs coerces the position filters to int and stores them back (:168-171)

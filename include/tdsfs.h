@@ -190,6 +190,16 @@ int tdsfs_check(tdsfs_t* ctx);
 /* One-call convenience used by the end-to-end benchmark: background(mode) -> finalize -> scan_bp. */
 int tdsfs_run_bp(tdsfs_t* ctx, int32_t bg_mode, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
 
+/* Legacy Poisson composite score of every fixed-bp window, the first-generation script's calculate_p_window
+ * (scripts/twoDSFS.py:385-463; the class copy :304-393 cannot run): per window the UNFOLDED 2D spectrum keyed by raw alt
+ * counts (twoDSFS.py:211-303: SNPs with both alt counts 0 skipped, a pseudo-count 1/total added to every bin), S_w = the sum
+ * of all its bins, and the sum over the bins with S_w q != 0 of poisson.logpmf(int(count), S_w q) (:336-374).
+ * q2d[(2n1+1)(2n2+1)] = the normalised background (normalize_2d_sfs :324-334).  Needs tdsfs_set_panel(..., fold = 0) and
+ * tdsfs_background (any mode: it writes the per-SNP bins).  Results: T2D = the score, n2d = SNPs counted in the spectrum,
+ * snp_count as in the other scans; the 1D fields are zero. */
+int tdsfs_set_poisson_background(tdsfs_t* ctx, const double* q2d);
+int tdsfs_scan_poisson_bp(tdsfs_t* ctx, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
+
 /* Spectra of one scanned window (calculate_2d_sfs / calculate_1d_sfs on window_data): dense outputs, any NULL. */
 int tdsfs_window_spectra(tdsfs_t* ctx, int64_t window, uint64_t* sfs2d, uint64_t* sfs1d_p1, uint64_t* sfs1d_p2);
 

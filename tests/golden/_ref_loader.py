@@ -31,6 +31,18 @@ def load_class():
     return ns["LikelihoodInference_jointSFS"]
 
 
+def load_legacy():
+    """The first-generation script scripts/twoDSFS.py (Poisson composite score): its FunctionDefs only -- the module level
+    opens /Users/... paths and imports matplotlib / pandas."""
+    path = f"{REF}/scripts/twoDSFS.py"
+    tree = ast.parse(open(path).read())
+    want = {"calculate_2d_sfs", "normalize_2d_sfs", "calculate_p", "count_snps", "calculate_p_window"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    ns = _ns()
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
 def load_sims():
     path = f"{REF}/scripts/sims_scan.py"
     tree = ast.parse(open(path).read())

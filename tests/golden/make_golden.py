@@ -14,6 +14,8 @@ Fixtures written:
                          scanner, spectrum builder and likelihood (class and sims_scan twins)
   ingest_small.vcf.gz, ingest_small.popmap.txt, ingest_small.json
                          hand-built VCF exercising the ingest gates + reference make_data_dict_vcf output
+  poisson_cases.json     seeded random data_dicts + the outputs of the first-generation script's Poisson window scan
+                         (scripts/twoDSFS.py: calculate_2d_sfs with pseudo-counts, normalize_2d_sfs, calculate_p_window)
   ecb_subset.vcf.gz, ecb_subset.popmap.txt, ecb_subset.json
                          first contigs of vcf_pruned/ECB_LDpruned.vcf.gz with the header-derived popmap
                           + reference outputs at 20 kb / 500 kb / 500-SNP
@@ -23,7 +25,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from _ref_loader import load_class, load_sims, REF  # noqa: E402
+from _ref_loader import load_class, load_sims, load_legacy, REF  # noqa: E402
 
 RefClass = load_class()
 sims = load_sims()
@@ -373,8 +375,38 @@ def do_ingest():
     print("ingest done", len(d))
 
 
+def do_poisson():
+    """scripts/twoDSFS.py:211-463 run unmodified: unfolded 2D spectrum with a 1/total pseudo-count on every bin, background
+    normalised over the interior, per-window sum of poisson.logpmf over the bins with a non-zero expectation."""
+    L = load_legacy()
+    rng = np.random.default_rng(20241007)
+    cases = []
+    specs = [  # chroms, n1, n2, snps per chrom, L, window, start, end, variant_type, background
+        (["c2", "c10", "c1"], 4, 3, 220, 9000, 1000, None, None, None, "genome"),
+        (["1"], 6, 5, 400, 30000, 2500, None, None, "A", "genome"),
+        (["7", "x"], 3, 3, 90, 12000, 3000, 2000, 9000, None, "genome"),
+        (["a", "b"], 5, 2, 150, 5000, 400, None, None, None, "other"),       # background from a different dict: zero-expectation bins
+        (["s"], 2, 2, 12, 60000, 5000, None, None, None, "genome"),           # sparse: one-SNP windows (the int(x + 1/1) quirk)
+        (["k1", "k2"], 8, 8, 700, 20000, 20000, None, None, None, "genome"),  # one big window per chromosome
+    ]
+    for chroms, n1, n2, nsnp, Lc, W, st, en, vt, bgk in specs:
+        d = rand_dict(rng, chroms, n1, n2, nsnp, Lc, miss=0.05)
+        src = d if bgk == "genome" else rand_dict(rng, chroms, n1, n2, max(nsnp // 3, 5), Lc, miss=0.05)
+        bg = L["calculate_2d_sfs"](src, "uv", "bv", n1, n2, None, None, None)
+        bgn = L["normalize_2d_sfs"](bg)
+        res = L["calculate_p_window"](d, bgn, W, "uv", "bv", n1, n2, st, en, vt)
+        cases.append(dict(n1=n1, n2=n2, W=W, start=st, end=en, variant_type=vt, rows=dict_to_rows(d, ("uv", "bv")),
+                          bg_rows=None if bgk == "genome" else dict_to_rows(src, ("uv", "bv")),
+                          bg_norm=[[k[0], k[1], jf(v)] for k, v in bgn.items()],
+                          windows=[[k, jf(v["p_values"]), v["snp_count"]] for k, v in res.items()]))
+    json.dump(dict(cases=cases), open(f"{HERE}/poisson_cases.json", "w"), allow_nan=True)
+    print("poisson done", [len(c["windows"]) for c in cases])
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["chr1", "small", "ingest"]
+    what = sys.argv[1:] or ["chr1", "small", "ingest", "poisson"]
+    if "poisson" in what:
+        do_poisson()
     if "chr1" in what:
         do_chr1()
     if "small" in what:
