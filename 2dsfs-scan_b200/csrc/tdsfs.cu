@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "tdsfs_kernels.cuh"
 #include "tdsfs_fused.cuh"
 
@@ -17,6 +19,13 @@ using namespace tdsfs;
 #define TDSFS_VERSION 200
 
 static thread_local std::string g_err;
+
+// NVTX range around every phase of the pass (count kernel, window boundaries, exchange, finalize, finish): visible to
+// Nsight Systems / Compute timelines, free when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -59,8 +68,8 @@ struct tdsfs_ctx {
   const uint32_t* dG = nullptr;
   bool own_G = false;
   // pooled device buffers reused across loads (sizes in bytes)
-  void *pool_G = nullptr, *pool_cnt = nullptr, *pool_pos = nullptr, *pool_flags = nullptr;
-  size_t cap_G = 0, cap_cnt = 0, cap_pos = 0, cap_flags = 0;
+  void *pool_G = nullptr, *pool_cnt = nullptr, *pool_pos = nullptr, *pool_flags = nullptr, *pool_off = nullptr, *pool_tmp = nullptr;
+  size_t cap_G = 0, cap_cnt = 0, cap_pos = 0, cap_flags = 0, cap_off = 0, cap_tmp = 0;
   int W1 = 0, W2 = 0, ns1 = 0, ns2 = 0;
   const uint16_t* dCnt = nullptr;
   bool own_cnt = false;
@@ -241,12 +250,14 @@ static int pool_get(void** pool, size_t* cap, size_t bytes, void** out) {
 }
 
 static void free_data(tdsfs_ctx* c) {
+  // a window plan that no scan consumed may still be reading the (pooled) position / offset arrays on the side stream
+  if (c->plan_W >= 0 && c->ev_plan) cudaStreamWaitEvent(c->stream, c->ev_plan, 0);
   c->dG = nullptr; c->dCnt = nullptr; c->dPos = nullptr; c->dFlags = nullptr;
   c->own_G = c->own_cnt = c->own_pos = c->own_flags = false;
   c->loaded = false;
   dev_free(c->dFix);
   c->nfix = 0;
-  dev_free(c->d_off);
+  c->d_off = nullptr;  // pooled (pool_off)
   for (auto& ch : c->chunks) if (ch.ev) cudaEventDestroy(ch.ev);
   c->chunks.clear();
   c->keys_ready = c->tables_ready = c->results_ready = false;
@@ -266,6 +277,8 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   if (c->pool_cnt) cudaFree(c->pool_cnt);
   if (c->pool_pos) cudaFree(c->pool_pos);
   if (c->pool_flags) cudaFree(c->pool_flags);
+  if (c->pool_off) cudaFree(c->pool_off);
+  if (c->pool_tmp) cudaFree(c->pool_tmp);
   peer_unmap(c);
   dev_free(c->d_peer_flags);
   dev_free(c->d_work);
@@ -345,7 +358,11 @@ static int load_common(tdsfs_ctx* c, long long S, const int32_t* pos, const long
   c->S = S;
   c->C = C;
   c->h_off.assign(chrom_off, chrom_off + C + 1);
-  CKR(dev_alloc(&c->d_off, C + 1));
+  {
+    void* d = nullptr;  // pooled: no cudaMalloc per load (the per-replicate sims path loads thousands of small panels)
+    CKR(pool_get(&c->pool_off, &c->cap_off, (size_t)(C + 1) * sizeof(long long), &d));
+    c->d_off = (long long*)d;
+  }
   CK(cudaMemcpyAsync(c->d_off, chrom_off, (size_t)(C + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   if (S > 0) CKR(adopt_or_upload(c, pos, S, &c->dPos, &c->own_pos, &c->pool_pos, &c->cap_pos));
   else {  // an empty shard (a rank of a sharded scan with no rows): a valid, empty position array
@@ -516,6 +533,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
   // background chromosome): the single-group histogram is still allocated and zeroed so that it can take part in the sum
   if (mode == TDSFS_BG_CHROM && (bg_chrom < -1 || bg_chrom >= c->C)) return fail(TDSFS_ERR_ARG, "background chromosome %d out of range", bg_chrom);
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:K1 count kernel (+ window sums)");
   cudaStream_t st = c->stream;
   CKR(peer_settle(c));  // peers may still be pushing the previous exchange into the histogram
   c->ws_ready = false;  // the records (and any window sums) are rewritten by this pass
@@ -676,6 +694,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
           q.nw1 = q.nw2 = 0;
         }
         q.pos_tma = (((uintptr_t)c->dPos) & 15) == 0 && !getenv("TDSFS_NO_POS_TMA");
+        q.snap_nearest = getenv("TDSFS_SNAP_BACK") ? 0 : 1;  // A/B knob
         // ring depth: as many stages per warp as asked for and as fit beside the histograms and the window tables
         const int per_warp_fixed = q.tab_words * 4;
         while (depth > 1 && p.cwarps * (depth * (stage_stride + 8) + per_warp_fixed) + hist_words * 4 + 16 > smem_max) --depth;
@@ -843,6 +862,7 @@ extern "C" int tdsfs_peer_allreduce_background(tdsfs_t* c) {
   if (c->d_hist != c->peer_exported_hist || c->NG != 1 || c->gstride != c->peer_words)
     return fail(TDSFS_ERR_STATE, "the histogram changed since tdsfs_peer_export (panel or background mode): export again");
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:exchange (peer all-reduce of the background)");
   cudaStream_t st = c->stream;
   PeerParams p;
   for (int r = 0; r < PEER_MAX; ++r) { p.hist[r] = c->peer_hist[r]; p.flags[r] = c->peer_flags[r]; }
@@ -876,6 +896,7 @@ extern "C" int tdsfs_peer_reduce_finalize(tdsfs_t* c) {
   if (c->d_hist != c->peer_exported_hist || c->NG != 1 || c->gstride != c->peer_words)
     return fail(TDSFS_ERR_STATE, "the histogram changed since tdsfs_peer_export (panel or background mode): export again");
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:exchange + finalize (one launch)");
   cudaStream_t st = c->stream;
   CKR(peer_settle(c));
   CKR(ensure_tables(c, 1));
@@ -942,8 +963,9 @@ extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double*
   for (int k = 1; k <= c->n1 - 1; ++k) B[1] += b1a[k];
   for (int k = 1; k <= c->n2 - 1; ++k) B[2] += b1b[k];
   for (int q = 0; q < 3; ++q) B[3 + q] = B[q] > 0.0 ? log(B[q]) : (B[q] == 0.0 ? -INFINITY : NAN);
-  double *t2 = nullptr, *t1a = nullptr, *t1b = nullptr;
-  CKR(dev_alloc(&t2, c->bins2d)); CKR(dev_alloc(&t1a, c->n1 + 1)); CKR(dev_alloc(&t1b, c->n2 + 1));
+  void* tmp = nullptr;  // pooled staging buffer for the three value vectors
+  CKR(pool_get(&c->pool_tmp, &c->cap_tmp, ((size_t)c->bins2d + c->n1 + 1 + c->n2 + 1) * sizeof(double), &tmp));
+  double *t2 = (double*)tmp, *t1a = t2 + c->bins2d, *t1b = t1a + c->n1 + 1;
   CK(cudaMemcpyAsync(t2, b2d, (size_t)c->bins2d * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(t1a, b1a, (size_t)(c->n1 + 1) * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(t1b, b1b, (size_t)(c->n2 + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -953,8 +975,7 @@ extern "C" int tdsfs_set_background(tdsfs_t* c, const double* b2d, const double*
   k_log_table<<<1, 256, 0, st>>>(t1b, c->d_lb1b, c->n2 + 1);
   c->launches += 3;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(st));
-  cudaFree(t2); cudaFree(t1a); cudaFree(t1b);
+  CK(cudaStreamSynchronize(st));  // the host vectors are the caller's: they may change after the call returns
   c->float_bg = true;
   c->poisson_bg = false;
   c->per_chrom_scoring = false;
@@ -999,6 +1020,7 @@ extern "C" int tdsfs_finalize_background(tdsfs_t* c) {
   if (c->tables_from_exchange && c->tables_ready) return 0;  // ... or by tdsfs_peer_reduce_finalize
   if (!c->keys_ready || c->bg_mode == TDSFS_BG_NONE) return fail(TDSFS_ERR_STATE, "no integer background to finalize");
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:finalize (ln tables)");
   cudaStream_t st = c->stream;
   CK(cudaEventRecord(c->ev[EV_FIN0], st));
   CKR(ensure_tables(c, c->NG));
@@ -1136,6 +1158,7 @@ static int plan(tdsfs_ctx* c, long long W, bool snp_mode) {
   if (!c || W < 1) return fail(TDSFS_ERR_ARG, "bad argument");
   if (!c->dPos) return fail(TDSFS_ERR_STATE, "load data first");
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:K2 window boundaries (side stream)");
   CKR(ensure_candidates(c, W, snp_mode, c->stream));     // the fused count kernel (main stream) reads the candidate offsets too
   CK(cudaEventRecord(c->ev_fork, c->stream));            // after everything queued so far (previous scan reads the old plan)
   CK(cudaStreamWaitEvent(c->plan_stream, c->ev_fork, 0));
@@ -1157,6 +1180,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
   if (!c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
   if (!c->tables_ready) return fail(TDSFS_ERR_STATE, "tdsfs_finalize_background / tdsfs_set_background first");
   CK(cudaSetDevice(c->device));
+  NvtxRange nvtx("tdsfs:K3 window statistics");
   cudaStream_t st = c->stream;
   const bool planned = c->plan_W == W && c->plan_snp == (int)snp_mode;
   c->plan_W = -1;
@@ -1198,11 +1222,14 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       f.use_smem = c->fmt.narrow && !c->per_chrom_scoring && c->R1 >= CORNER && c->R2 >= CORNER && tab_bytes <= 96 * 1024;
       f.large_ctas = c->large_ctas;
       const int smem = f.use_smem ? (int)tab_bytes : 0;
-      CK(cudaFuncSetAttribute(k3_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      bool stream_mode = false;  // measured (profiles/README.md round 2): round-robin windows with prefetched bounds vs one stream per warp
+      if (const char* e = getenv("TDSFS_FINISH_STREAM")) stream_mode = atoi(e) != 0;
+      void (*fk)(FinishParams) = stream_mode ? k3_finish<true> : k3_finish<false>;
+      CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 1;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_finish, 256, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, 256, smem));
       const int grid = (int)std::max<long long>(1, std::min<long long>((ncand + 7) / 8, (long long)c->sm_count * std::max(1, occ)));
-      k3_finish<<<grid, 256, smem, st>>>(f);
+      fk<<<grid, 256, smem, st>>>(f);
       c->launches++;
       c->last_fused = true;
       CK(cudaEventRecord(c->ev[EV_K3S], st));

@@ -35,6 +35,7 @@ struct FusedParams {
   int pos_tma;                // the tile's positions ride the TMA ring (16-byte aligned position array)
   int tab_words;              // per-warp window tables: HASH_SLOTS + packed 1D words, a multiple of 4
   int nw1, nw2;               // packed 1D words per population: (n + 2) / 2
+  int snap_nearest;           // range boundaries snap to the nearest window start (0: back to the start of the window that holds them)
 };
 
 // dx[m] = (m+1) ln(m+1) - m ln m, written as ln(m+1) + m log1p(1/m) so that no large terms cancel
@@ -230,14 +231,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
     const int hi_clamp = r1 < S ? snap_row(q, r1, sth, lane, false) : S;
     int slo = lo_clamp, shi = hi_clamp;
     if (j > 0) {
-      slo = snap_row(q, target(j), st0, lane, true);
+      slo = snap_row(q, target(j), st0, lane, q.snap_nearest != 0);
       if (slo <= lo_clamp) { slo = lo_clamp; st0 = stl; }
       if (slo >= hi_clamp) { slo = hi_clamp; st0 = sth; }
     } else {
       st0 = stl;
     }
     if (j + 1 < nparts) {
-      shi = snap_row(q, target(j + 1), st1, lane, true);
+      shi = snap_row(q, target(j + 1), st1, lane, q.snap_nearest != 0);
       if (shi <= lo_clamp) shi = lo_clamp;
       if (shi >= hi_clamp) shi = hi_clamp;
     }
@@ -561,7 +562,10 @@ __device__ __forceinline__ void finish_window(const ScoreParams& p, long long id
   }
 }
 
-__global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ FinishParams q) {
+// STREAM = every warp owns a contiguous range of windows and reads their records as one stream (next batch always in
+// flight); otherwise windows are dealt out round-robin and each is read on its own (the next window's bounds prefetched).
+template <bool STREAM>
+__global__ void __launch_bounds__(256, STREAM ? 3 : 4) k3_finish(const __grid_constant__ FinishParams q) {
   // ln b of group 0 staged per CTA: [64 x 64] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
   // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
   // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch
@@ -580,11 +584,60 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
     for (int i = threadIdx.x; i <= 2 * p.n1; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n1); s_a[i] = f ? __ldg(p.lb1a + f) : 0.0; }
     for (int i = threadIdx.x; i <= 2 * p.n2; i += blockDim.x) { const uint32_t f = fold_fast(i, p.n2); s_b[i] = f ? __ldg(p.lb1b + f) : 0.0; }
     __syncthreads();
+    const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
+    const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec);
+    // ln b of one decoded record: the three table reads
+    auto lookup = [&](uint32_t rr, double& l2, double& la, double& lb) {
+      const uint32_t k1 = rr & m1, k2 = (rr >> sh2) & m2;
+      const uint32_t a1 = k1 + 2u * ((rr >> shd1) & md), a2 = k2 + 2u * (rr >> shd2);
+      if ((k1 | k2) < (uint32_t)CORNER) {
+        l2 = s_c[(k1 << 6) | k2];
+      } else {
+        const uint32_t key = k1 * (uint32_t)p.C2 + k2;
+        l2 = key != last ? __ldg(p.lb2 + key) : 0.0;
+      }
+      la = s_a[a1];
+      lb = s_b[a2];
+    };
+    if (!STREAM) {
+      constexpr int Q = 8;  // records per lane in flight
+      long long id = wid;
+      int lo = 0, hi = 0;
+      if (id < p.ncand) { lo = __ldg(p.wlo + id); hi = __ldg(p.whi + id); }
+      while (id < p.ncand) {
+        const long long nid = id + nwarp;  // the next window's bounds, ahead of their use
+        int nlo = 0, nhi = 0;
+        if (nid < p.ncand) { nlo = __ldg(p.wlo + nid); nhi = __ldg(p.whi + nid); }
+        const int cnt = hi - lo;
+        if (cnt > 0 && cnt <= WCAP) {  // empty: flagged by K2; large: the CTA path below
+          const double wsv = __ldg(q.ws + id * 4 + (lane & 3));
+          double g2 = 0.0, g1a = 0.0, g1b = 0.0;
+          for (int base = 0; base < cnt; base += Q * 32) {
+            uint32_t r[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+              const int i = base + j * 32 + lane;
+              r[j] = i < cnt ? __ldcs(rec + lo + i) : 0u;  // 0 decodes to the skipped bin: every table holds 0 there
+            }
+#pragma unroll
+            for (int h4 = 0; h4 < Q; h4 += 4) {
+              double l2[4], la[4], lb[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+            }
+          }
+          g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
+          finish_window(p, id, lo, cnt, g2, g1a, g1b, wsv, p.lb2, p.lb1a, p.lb1b, p.B, lane);
+        }
+        id = nid; lo = nlo; hi = nhi;
+      }
+    } else {
     // Every warp owns a CONTIGUOUS range of candidate windows, hence a contiguous stream of records: it reads the stream in
     // batches of 256 records (the next batch is always in flight while the current one is processed) and cuts it into
     // windows as it goes.
-    const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
-    const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
     const long long wa = p.ncand * wid / nwarp, wb = p.ncand * (wid + 1) / nwarp;
     // first valid (non-empty, at most WCAP SNPs) window at or after `from`
     auto seek = [&](long long from, int& lo, int& hi) -> long long {
@@ -599,7 +652,6 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
     int lo = 0, hi = 0;
     long long id = seek(wa, lo, hi);
     if (id < wb) {
-      const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec);
       const int s_end = __ldg(p.whi + wb - 1);  // rows of this warp's windows end here (whi is non-decreasing)
       constexpr int Q = 8;
       uint32_t rn[Q];
@@ -610,8 +662,10 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
         rn[j] = row < s_end ? __ldcs(rec + row) : 0u;
       }
       double wsv = __ldg(q.ws + id * 4 + (lane & 3));
-      int nlo = 0, nhi = 0;  // the window after the current one, looked up ahead of its use
-      long long nid = seek(id + 1, nlo, nhi);
+      // the bounds of the candidate after the current window are loaded ahead of their use and only looked at when the
+      // current window closes (if that candidate is empty or too large, `seek` walks on from there)
+      int nlo = 0, nhi = 0;
+      if (id + 1 < wb) { nlo = __ldg(p.wlo + id + 1); nhi = __ldg(p.whi + id + 1); }
       double g2 = 0.0, g1a = 0.0, g1b = 0.0;
       while (id < wb) {
         uint32_t r[Q];
@@ -630,19 +684,7 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
         for (int h4 = 0; h4 < Q; h4 += 4) {
           double l2[4], la[4], lb[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t rr = r[h4 + j];
-            const uint32_t k1 = rr & m1, k2 = (rr >> sh2) & m2;
-            const uint32_t a1 = k1 + 2u * ((rr >> shd1) & md), a2 = k2 + 2u * (rr >> shd2);
-            if ((k1 | k2) < (uint32_t)CORNER) {
-              l2[j] = s_c[(k1 << 6) | k2];
-            } else {
-              const uint32_t key = k1 * (uint32_t)p.C2 + k2;
-              l2[j] = key != last ? __ldg(p.lb2 + key) : 0.0;
-            }
-            la[j] = s_a[a1];
-            lb[j] = s_b[a2];
-          }
+          for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rb = cur + (h4 + j) * 32;  // first row of this sub-row
@@ -660,16 +702,19 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
               g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
               finish_window(p, id, lo, hi - lo, g2, g1a, g1b, wsv, p.lb2, p.lb1a, p.lb1b, p.B, lane);
               g2 = g1a = g1b = 0.0;
-              id = nid; lo = nlo; hi = nhi;
+              ++id;
+              lo = nlo; hi = nhi;
+              if (id < wb && !(hi > lo && hi - lo <= WCAP)) id = seek(id, lo, hi);  // empty or large candidate: walk on
               if (id < wb) {
                 wsv = __ldg(q.ws + id * 4 + (lane & 3));
-                nid = seek(id + 1, nlo, nhi);
+                if (id + 1 < wb) { nlo = __ldg(p.wlo + id + 1); nhi = __ldg(p.whi + id + 1); }
               }
             }
           }
         }
         if (cur >= s_end) break;  // a batch past the end only closes a window that ended exactly on the previous batch's last row
       }
+    }
     }
   } else {
     for (long long id = wid; id < p.ncand; id += nwarp) {
