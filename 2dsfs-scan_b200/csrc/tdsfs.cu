@@ -624,11 +624,9 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       // Ring geometry (measured, profiles/README.md "K1 ring geometry"): ONE stage per warp and about 128 KB of tiles in
       // flight per SM.  Rows up to 8 KB per block use two-block tiles; more warps for narrow rows (more per-SNP work per
       // byte), fewer and larger requests for wide rows.  Deeper rings and more bytes in flight are slower on B200.
-      // fused kernel (measured, profiles/README.md round 2): as many warps as fit (it is bound by per-warp instruction latency,
-      // not by bytes in flight) with tiles of about 8 KB; the plain count kernel keeps the round-1 rule (128 KB in flight)
-      p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile
-      if (const char* e = getenv("TDSFS_K1_TILE")) p.tile_blocks = std::max(1, atoi(e));  // tuning knob: blocks per tile
-      p.stage_bytes = p.tile_blocks * blk_bytes;
+      // fused kernel (measured, profiles/README.md round 2): it is bound by per-warp instruction latency, not by bytes in
+      // flight, so it takes as many warps as fit, with tiles of at most 8 KB halved until the warp limit is reached
+      // (config 5: 14 warps x 8 KB, config 4: 24 warps x 3.5 KB); the plain count kernel keeps the round-1 rule (128 KB in flight)
       const bool old_kernel = getenv("TDSFS_K1_OLD") != nullptr || getenv("TDSFS_K1_PROBE") != nullptr;  // A/B + bandwidth probe
       // ---- fused scan: a plan for (W, mode) is pending -> the count kernel also leaves every window's background-independent sums
       FusedParams q;
@@ -636,15 +634,23 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       const int hist_words = (p.cr * p.cc + p.h1a + p.h1b + 3) & ~3;
       q.nw1 = (c->n1 + 2) / 2; q.nw2 = (c->n2 + 2) / 2;
       const int tab_words = HASH_SLOTS + ((q.nw1 + q.nw2 + 3) & ~3);
-      const int stage_stride = p.stage_bytes + p.tile_blocks * BLK * 4;
       const int smem_max = 227 * 1024;
       bool fuse = !old_kernel && c->plan_W > 0 && c->plan_W <= 0x7FFFFFFFLL && score_small_ok(c->n1, c->n2, c->bins2d) &&
                   !(c->plan_snp && c->plan_W > WCAP) && !getenv("TDSFS_NO_FUSE");
-      int fit = (smem_max - hist_words * 4 - 16) / (stage_stride + 8 + (fuse ? tab_words * 4 : 0));
-      if (fuse && fit < 4) {  // panel too large for warp-private window tables beside the ring: plain count kernel + the table scorer
-        fuse = false;
-        fit = (smem_max - hist_words * 4 - 16) / (stage_stride + 8);
-      }
+      auto fit_for = [&](int tile_blocks, bool with_tables) {
+        const int stride = tile_blocks * blk_bytes + tile_blocks * BLK * 4;
+        return (smem_max - hist_words * 4 - 16) / (stride + 8 + (with_tables ? tab_words * 4 : 0));
+      };
+      p.tile_blocks = std::max(1, 8192 / blk_bytes);  // one TMA bulk copy per tile
+      if (fuse && fit_for(1, true) < 4) fuse = false;  // panel too large for warp-private window tables beside the ring: table scorer
+      if (fuse)
+        while (p.tile_blocks > 1 && fit_for(p.tile_blocks, true) < K1_CWARPS) p.tile_blocks /= 2;
+      else if (blk_bytes <= 8192)
+        p.tile_blocks = std::max(2, p.tile_blocks);
+      if (const char* e = getenv("TDSFS_K1_TILE")) p.tile_blocks = std::max(1, atoi(e));  // tuning knob: blocks per tile
+      p.stage_bytes = p.tile_blocks * blk_bytes;
+      const int stage_stride = p.stage_bytes + p.tile_blocks * BLK * 4;
+      const int fit = fit_for(p.tile_blocks, fuse);
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
       p.cwarps = fuse ? std::min(fit, K1_CWARPS) : std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
       if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
@@ -1224,7 +1230,9 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       const int smem = f.use_smem ? (int)tab_bytes : 0;
       bool stream_mode = false;  // measured (profiles/README.md round 2): round-robin windows with prefetched bounds vs one stream per warp
       if (const char* e = getenv("TDSFS_FINISH_STREAM")) stream_mode = atoi(e) != 0;
-      void (*fk)(FinishParams) = stream_mode ? k3_finish<true> : k3_finish<false>;
+      int minb = 4;  // CTAs per SM the kernel is compiled for (4: 64 registers, 3: 80)
+      if (const char* e = getenv("TDSFS_FINISH_OCC")) minb = atoi(e) == 3 ? 3 : 4;
+      void (*fk)(FinishParams) = stream_mode ? k3_finish<true, 3> : (minb == 3 ? k3_finish<false, 3> : k3_finish<false, 4>);
       CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 1;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, 256, smem));

@@ -564,8 +564,8 @@ __device__ __forceinline__ void finish_window(const ScoreParams& p, long long id
 
 // STREAM = every warp owns a contiguous range of windows and reads their records as one stream (next batch always in
 // flight); otherwise windows are dealt out round-robin and each is read on its own (the next window's bounds prefetched).
-template <bool STREAM>
-__global__ void __launch_bounds__(256, STREAM ? 3 : 4) k3_finish(const __grid_constant__ FinishParams q) {
+template <bool STREAM, int MINB>
+__global__ void __launch_bounds__(256, MINB) k3_finish(const __grid_constant__ FinishParams q) {
   // ln b of group 0 staged per CTA: [64 x 64] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
   // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
   // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch
@@ -601,38 +601,65 @@ __global__ void __launch_bounds__(256, STREAM ? 3 : 4) k3_finish(const __grid_co
       lb = s_b[a2];
     };
     if (!STREAM) {
-      constexpr int Q = 8;  // records per lane in flight
-      long long id = wid;
-      int lo = 0, hi = 0;
-      if (id < p.ncand) { lo = __ldg(p.wlo + id); hi = __ldg(p.whi + id); }
+      // Windows dealt out round-robin; software pipeline over windows: while window i is processed, the first 256 records of
+      // window i + 1 and the bounds of window i + 2 are in flight; a window's records beyond the first 256 are requested at
+      // its start (one more batch) or on demand (above 512).
+      constexpr int Q = 8;  // records per lane and batch
+      auto bounds = [&](long long w, int& lo, int& cnt) {
+        lo = 0; cnt = 0;
+        if (w < p.ncand) {
+          lo = __ldg(p.wlo + w);
+          const int c = __ldg(p.whi + w) - lo;
+          cnt = c <= WCAP ? c : 0;  // large windows are scored by the CTA path below
+        }
+      };
+      auto load_batch = [&](uint32_t (&r)[Q], int lo, int cnt, int base) {
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          const int i = base + j * 32 + lane;
+          r[j] = i < cnt ? __ldcs(rec + lo + i) : 0u;  // 0 decodes to the skipped bin: every table holds 0 there
+        }
+      };
+      double g2 = 0.0, g1a = 0.0, g1b = 0.0;
+      auto consume = [&](const uint32_t (&r)[Q]) {
+#pragma unroll
+        for (int h4 = 0; h4 < Q; h4 += 4) {
+          double l2[4], la[4], lb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+        }
+      };
+      long long id = wid, nid = wid + nwarp;
+      int lo, cnt, nlo, ncnt;
+      bounds(id, lo, cnt);
+      bounds(nid, nlo, ncnt);
+      uint32_t rn[Q];
+      load_batch(rn, lo, cnt, 0);
       while (id < p.ncand) {
-        const long long nid = id + nwarp;  // the next window's bounds, ahead of their use
-        int nlo = 0, nhi = 0;
-        if (nid < p.ncand) { nlo = __ldg(p.wlo + nid); nhi = __ldg(p.whi + nid); }
-        const int cnt = hi - lo;
-        if (cnt > 0 && cnt <= WCAP) {  // empty: flagged by K2; large: the CTA path below
+        uint32_t r[Q], r2[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) r[j] = rn[j];
+        if (cnt > Q * 32) load_batch(r2, lo, cnt, Q * 32);
+        const long long nnid = nid + nwarp;
+        int nnlo, nncnt;
+        bounds(nnid, nnlo, nncnt);
+        load_batch(rn, nlo, ncnt, 0);
+        if (cnt > 0) {
           const double wsv = __ldg(q.ws + id * 4 + (lane & 3));
-          double g2 = 0.0, g1a = 0.0, g1b = 0.0;
-          for (int base = 0; base < cnt; base += Q * 32) {
-            uint32_t r[Q];
-#pragma unroll
-            for (int j = 0; j < Q; ++j) {
-              const int i = base + j * 32 + lane;
-              r[j] = i < cnt ? __ldcs(rec + lo + i) : 0u;  // 0 decodes to the skipped bin: every table holds 0 there
-            }
-#pragma unroll
-            for (int h4 = 0; h4 < Q; h4 += 4) {
-              double l2[4], la[4], lb[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
-            }
+          g2 = g1a = g1b = 0.0;
+          consume(r);
+          if (cnt > Q * 32) consume(r2);
+          if (cnt > 2 * Q * 32) {
+            load_batch(r2, lo, cnt, 2 * Q * 32);
+            consume(r2);
           }
           g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
           finish_window(p, id, lo, cnt, g2, g1a, g1b, wsv, p.lb2, p.lb1a, p.lb1b, p.B, lane);
         }
-        id = nid; lo = nlo; hi = nhi;
+        id = nid; lo = nlo; cnt = ncnt;
+        nid = nnid; nlo = nnlo; ncnt = nncnt;
       }
     } else {
     // Every warp owns a CONTIGUOUS range of candidate windows, hence a contiguous stream of records: it reads the stream in
