@@ -150,6 +150,14 @@ struct tdsfs_ctx {
   unsigned long long* d_work = nullptr;  // window hand-out counter of the scorer (monotonic, never reset)
   unsigned long long work_base = 0;
   bool results_ready = false;
+  // whole asynchronous pass captured as a CUDA graph (tdsfs_step_bp): replayed while nothing it depends on changes
+  unsigned long long generation = 0;  // bumped by every load / panel / stream / peer change
+  cudaGraphExec_t step_exec = nullptr;
+  unsigned long long step_gen = 0, warm_gen = 0;
+  long long step_W = -1, warm_W = -1;
+  int step_mode = -1, warm_mode = -1;
+  long long step_launches = 0;
+  bool step_graphs_off = false;       // capture failed once: run eagerly from then on
   // instrumentation
   cudaEvent_t ev[NEV] = {};
   float ms[10] = {};
@@ -249,7 +257,14 @@ static int pool_get(void** pool, size_t* cap, size_t bytes, void** out) {
   return 0;
 }
 
+static void drop_step_graph(tdsfs_ctx* c) {
+  if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
+  c->step_exec = nullptr;
+  c->generation++;
+}
+
 static void free_data(tdsfs_ctx* c) {
+  drop_step_graph(c);
   // a window plan that no scan consumed may still be reading the (pooled) position / offset arrays on the side stream
   if (c->plan_W >= 0 && c->ev_plan) cudaStreamWaitEvent(c->stream, c->ev_plan, 0);
   c->dG = nullptr; c->dCnt = nullptr; c->dPos = nullptr; c->dFlags = nullptr;
@@ -272,6 +287,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  drop_step_graph(c);
   free_data(c);
   if (c->pool_G) cudaFree(c->pool_G);
   if (c->pool_cnt) cudaFree(c->pool_cnt);
@@ -301,6 +317,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
 extern "C" int tdsfs_set_stream(tdsfs_t* c, void* s) {
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
   c->stream = s ? (cudaStream_t)s : c->own_stream;
+  drop_step_graph(c);
   return 0;
 }
 
@@ -316,6 +333,7 @@ extern "C" int tdsfs_set_panel(tdsfs_t* c, int32_t n1, int32_t n2, int32_t fold)
   long long bins = (long long)(2 * n1 + 1) * (2 * n2 + 1);
   if (bins > 0x7FFFFFFFLL) return fail(TDSFS_ERR_ARG, "2D spectrum too large: (2 n1 + 1)(2 n2 + 1) = %lld bins exceeds 2^31 - 1", bins);
   CK(cudaSetDevice(c->device));
+  drop_step_graph(c);
   c->n1 = n1; c->n2 = n2; c->fold = fold != 0;
   c->R1 = 2 * n1 + 1; c->R2 = 2 * n2 + 1; c->bins2d = (int)bins;
   c->keys_ready = c->tables_ready = c->results_ready = false;
@@ -794,6 +812,7 @@ static int peer_settle(tdsfs_ctx* c) {
 }
 
 static void peer_unmap(tdsfs_ctx* c) {
+  drop_step_graph(c);
   for (int r = 0; r < c->peer_world; ++r) {
     if (r != c->peer_rank) {
       if (c->peer_hist[r]) cudaIpcCloseMemHandle(c->peer_hist[r]);
@@ -859,6 +878,7 @@ extern "C" int tdsfs_peer_import(tdsfs_t* c, const void* blobs) {
     c->peer_flags[r] = (unsigned long long*)pf;
   }
   c->peer_ready = true;
+  drop_step_graph(c);
   return 0;
 }
 
@@ -1228,11 +1248,7 @@ static int scan(tdsfs_ctx* c, long long W, bool snp_mode, tdsfs_result_t* out, i
       f.use_smem = c->fmt.narrow && !c->per_chrom_scoring && c->R1 >= CORNER && c->R2 >= CORNER && tab_bytes <= 96 * 1024;
       f.large_ctas = c->large_ctas;
       const int smem = f.use_smem ? (int)tab_bytes : 0;
-      bool stream_mode = false;  // measured (profiles/README.md round 2): round-robin windows with prefetched bounds vs one stream per warp
-      if (const char* e = getenv("TDSFS_FINISH_STREAM")) stream_mode = atoi(e) != 0;
-      int minb = 4;  // CTAs per SM the kernel is compiled for (4: 64 registers, 3: 80)
-      if (const char* e = getenv("TDSFS_FINISH_OCC")) minb = atoi(e) == 3 ? 3 : 4;
-      void (*fk)(FinishParams) = stream_mode ? k3_finish<true, 3> : (minb == 3 ? k3_finish<false, 3> : k3_finish<false, 4>);
+      void (*fk)(FinishParams) = k3_finish;
       CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 1;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, 256, smem));
@@ -1327,6 +1343,63 @@ extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result
     if (!r) r = tdsfs_finalize_background(c);
     if (!r) r = scan(c, W, false, out, cap, n);
     if (!r) r = tdsfs_check(c);
+  }
+  c->sync = was_sync;
+  return r;
+}
+
+// One whole ASYNCHRONOUS pass on the handle's stream: window plan (side stream) -> count kernel -> exchange + ln tables (one
+// launch when the peer exchange is mapped, else finalize) -> finish kernel.  The second call with the same arguments on the
+// same data captures the pass as a CUDA graph; later calls replay it (one launch instead of ~10 API calls, and the gaps
+// between dependent kernels shrink).  Results stay on the device (tdsfs_fetch_results); errors surface in tdsfs_check.
+static int step_eager(tdsfs_ctx* c, int32_t bg_mode, int64_t W) {
+  CKR(plan(c, W, false));
+  CKR(tdsfs_background(c, bg_mode, 0, -1, -1));
+  if (c->peer_ready && c->NG == 1 && (bg_mode == TDSFS_BG_GENOME || bg_mode == TDSFS_BG_CHROM)) CKR(tdsfs_peer_reduce_finalize(c));
+  else CKR(tdsfs_finalize_background(c));
+  return scan(c, W, false, nullptr, 0, nullptr);
+}
+
+extern "C" int tdsfs_step_bp(tdsfs_t* c, int32_t bg_mode, int64_t W) {
+  if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");
+  if (!c->loaded) return fail(TDSFS_ERR_STATE, "load data first");
+  CK(cudaSetDevice(c->device));
+  const bool was_sync = c->sync;
+  c->sync = false;
+  int r = 0;
+  bool device_resident = true;
+  for (auto& ch : c->chunks) if (ch.ev) device_resident = false;  // a host upload in flight is not part of a replayable pass
+  if (c->step_exec && c->step_gen == c->generation && c->step_W == W && c->step_mode == bg_mode) {
+    NvtxRange nvtx("tdsfs:step (graph replay)");
+    cudaError_t e = cudaGraphLaunch(c->step_exec, c->stream);
+    if (e != cudaSuccess) r = fail(TDSFS_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+    c->launches += c->step_launches;
+  } else if (!c->step_graphs_off && device_resident && !getenv("TDSFS_NO_GRAPH") && c->warm_gen == c->generation && c->warm_W == W &&
+             c->warm_mode == bg_mode) {
+    // the previous call ran the same pass eagerly (every buffer is allocated): capture this one
+    const long long l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+    if (e == cudaSuccess) {
+      r = step_eager(c, bg_mode, W);
+      e = cudaStreamEndCapture(c->stream, &graph);
+      if (!r && e == cudaSuccess && graph) e = cudaGraphInstantiate(&c->step_exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (r || e != cudaSuccess || !c->step_exec) {  // capture not possible here: stay eager
+      cudaGetLastError();
+      if (c->step_exec) { cudaGraphExecDestroy(c->step_exec); c->step_exec = nullptr; }
+      c->step_graphs_off = true;
+      r = step_eager(c, bg_mode, W);
+    } else {
+      c->step_gen = c->generation; c->step_W = W; c->step_mode = bg_mode;
+      c->step_launches = c->launches - l0;
+      e = cudaGraphLaunch(c->step_exec, c->stream);
+      if (e != cudaSuccess) r = fail(TDSFS_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+    }
+  } else {
+    r = step_eager(c, bg_mode, W);
+    c->warm_gen = c->generation; c->warm_W = W; c->warm_mode = bg_mode;
   }
   c->sync = was_sync;
   return r;

@@ -562,10 +562,7 @@ __device__ __forceinline__ void finish_window(const ScoreParams& p, long long id
   }
 }
 
-// STREAM = every warp owns a contiguous range of windows and reads their records as one stream (next batch always in
-// flight); otherwise windows are dealt out round-robin and each is read on its own (the next window's bounds prefetched).
-template <bool STREAM, int MINB>
-__global__ void __launch_bounds__(256, MINB) k3_finish(const __grid_constant__ FinishParams q) {
+__global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ FinishParams q) {
   // ln b of group 0 staged per CTA: [64 x 64] the low-count corner of the 2D table, entry 0 (the skipped bin) = 0, then the 1D
   // tables indexed by the UNFOLDED count a = k + 2 d of the narrow record (ln b[fold(a)], 0 where the SNP is not in the 1D
   // likelihood): the per-SNP work is two shifts, three table reads and three adds, without a fold or a validity branch
@@ -600,7 +597,7 @@ __global__ void __launch_bounds__(256, MINB) k3_finish(const __grid_constant__ F
       la = s_a[a1];
       lb = s_b[a2];
     };
-    if (!STREAM) {
+    {
       // Windows dealt out round-robin; software pipeline over windows: while window i is processed, the first 256 records of
       // window i + 1 and the bounds of window i + 2 are in flight; a window's records beyond the first 256 are requested at
       // its start (one more batch) or on demand (above 512).
@@ -661,87 +658,6 @@ __global__ void __launch_bounds__(256, MINB) k3_finish(const __grid_constant__ F
         id = nid; lo = nlo; cnt = ncnt;
         nid = nnid; nlo = nnlo; ncnt = nncnt;
       }
-    } else {
-    // Every warp owns a CONTIGUOUS range of candidate windows, hence a contiguous stream of records: it reads the stream in
-    // batches of 256 records (the next batch is always in flight while the current one is processed) and cuts it into
-    // windows as it goes.
-    const long long wa = p.ncand * wid / nwarp, wb = p.ncand * (wid + 1) / nwarp;
-    // first valid (non-empty, at most WCAP SNPs) window at or after `from`
-    auto seek = [&](long long from, int& lo, int& hi) -> long long {
-      while (from < wb) {
-        lo = __ldg(p.wlo + from);
-        hi = __ldg(p.whi + from);
-        if (hi > lo && hi - lo <= WCAP) break;
-        ++from;
-      }
-      return from;
-    };
-    int lo = 0, hi = 0;
-    long long id = seek(wa, lo, hi);
-    if (id < wb) {
-      const int s_end = __ldg(p.whi + wb - 1);  // rows of this warp's windows end here (whi is non-decreasing)
-      constexpr int Q = 8;
-      uint32_t rn[Q];
-      int base = lo;  // row of lane 0, sub-row 0 of the batch in `rn`
-#pragma unroll
-      for (int j = 0; j < Q; ++j) {
-        const int row = base + j * 32 + lane;
-        rn[j] = row < s_end ? __ldcs(rec + row) : 0u;
-      }
-      double wsv = __ldg(q.ws + id * 4 + (lane & 3));
-      // the bounds of the candidate after the current window are loaded ahead of their use and only looked at when the
-      // current window closes (if that candidate is empty or too large, `seek` walks on from there)
-      int nlo = 0, nhi = 0;
-      if (id + 1 < wb) { nlo = __ldg(p.wlo + id + 1); nhi = __ldg(p.whi + id + 1); }
-      double g2 = 0.0, g1a = 0.0, g1b = 0.0;
-      while (id < wb) {
-        uint32_t r[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) r[j] = rn[j];
-        const int cur = base;
-        base += Q * 32;
-        if (base < s_end) {
-#pragma unroll
-          for (int j = 0; j < Q; ++j) {
-            const int row = base + j * 32 + lane;
-            rn[j] = row < s_end ? __ldcs(rec + row) : 0u;
-          }
-        }
-#pragma unroll
-        for (int h4 = 0; h4 < Q; h4 += 4) {
-          double l2[4], la[4], lb[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int rb = cur + (h4 + j) * 32;  // first row of this sub-row
-            const int row = rb + lane;
-            while (id < wb) {
-              if (rb >= lo && rb + 32 <= hi) {  // the whole sub-row lies inside the current window
-                g2 += l2[j]; g1a += la[j]; g1b += lb[j];
-                break;
-              }
-              if (rb + 32 <= lo) break;         // before the current window (rows of a skipped window)
-              const bool in = row >= lo && row < hi;
-              g2 += in ? l2[j] : 0.0; g1a += in ? la[j] : 0.0; g1b += in ? lb[j] : 0.0;
-              if (hi > rb + 32) break;          // the window continues in the next sub-row
-              // the current window ends inside this sub-row: finish it, move to the next one
-              g2 = warp_sum(g2); g1a = warp_sum(g1a); g1b = warp_sum(g1b);
-              finish_window(p, id, lo, hi - lo, g2, g1a, g1b, wsv, p.lb2, p.lb1a, p.lb1b, p.B, lane);
-              g2 = g1a = g1b = 0.0;
-              ++id;
-              lo = nlo; hi = nhi;
-              if (id < wb && !(hi > lo && hi - lo <= WCAP)) id = seek(id, lo, hi);  // empty or large candidate: walk on
-              if (id < wb) {
-                wsv = __ldg(q.ws + id * 4 + (lane & 3));
-                if (id + 1 < wb) { nlo = __ldg(p.wlo + id + 1); nhi = __ldg(p.whi + id + 1); }
-              }
-            }
-          }
-        }
-        if (cur >= s_end) break;  // a batch past the end only closes a window that ended exactly on the previous batch's last row
-      }
-    }
     }
   } else {
     for (long long id = wid; id < p.ncand; id += nwarp) {

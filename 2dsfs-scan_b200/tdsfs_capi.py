@@ -19,7 +19,7 @@ EXPORTS = [
     "tdsfs_create", "tdsfs_destroy", "tdsfs_last_error", "tdsfs_set_stream", "tdsfs_set_sync", "tdsfs_set_panel",
     "tdsfs_load_counts", "tdsfs_load_genotypes", "tdsfs_background", "tdsfs_background_device", "tdsfs_get_background",
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
-    "tdsfs_scan_snp", "tdsfs_set_poisson_background", "tdsfs_scan_poisson_bp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
+    "tdsfs_scan_snp", "tdsfs_set_poisson_background", "tdsfs_scan_poisson_bp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_step_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_reduce_finalize", "tdsfs_peer_close",
     "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_version",
 ]
@@ -259,6 +259,10 @@ class Handle:
         arrs, r = self._alloc_result(cap)
         self._check(self._L.tdsfs_run_bp(self._h, C.c_int32(bg_mode), C.c_int64(W), C.byref(r), C.c_int64(cap), C.byref(n)))
         return {k: v[:n.value] for k, v in arrs.items()}
+
+    def step_bp(self, bg_mode, W):
+        """One whole asynchronous pass (CUDA graph after the first two calls); results stay on the device."""
+        self._check(self._L.tdsfs_step_bp(self._h, C.c_int32(bg_mode), C.c_int64(W)))
 
     def window_spectra(self, window):
         R1, R2 = 2 * self.n1 + 1, 2 * self.n2 + 1

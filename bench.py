@@ -344,9 +344,15 @@ def measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, do_
         else:
             dist.all_reduce(hist_tensor())
 
+    use_graph = not args.no_graph
+
     def device_step():
-        """plan (K2 on a side stream, arms the fused count kernel) + count kernel (+ all-reduce of the background) + finalize
-        + finish kernel, all enqueued on one stream, no host sync."""
+        """One whole pass, enqueued on one stream with no host sync: plan (K2 on a side stream, arms the fused count kernel) +
+        count kernel + (exchange of the background +) ln tables + finish kernel.  tdsfs_step_bp replays the pass as a CUDA
+        graph from its third call on; with the NCCL exchange (a torch call in the middle) the pass is enqueued call by call."""
+        if use_graph and (world == 1 or peer["on"]):
+            h.step_bp(T.BG_GENOME, W)
+            return
         h.plan(W)
         h.background(T.BG_GENOME)
         if world > 1:
@@ -585,7 +591,7 @@ def run_b200(args, cfg):
                        + ((", all-reduced in place by the library's peer-memory kernel (CUDA IPC over NVLink, uint32 sum)" if m["peer"]
                           else ", all-reduced (NCCL, uint32 sum)") if world > 1 else ""), "row_bytes": m["RW"] * 4,
                        "scan_path": ("fused: k1_fused (window sums under the count kernel) + k3_finish" if m["fused"] else "table scorer")
-                       + f", {m['rec_bytes']}-byte per-SNP records",
+                       + f", {m['rec_bytes']}-byte per-SNP records" + ("" if args.no_graph else ", pass replayed as a CUDA graph (tdsfs_step_bp)"),
                        "generator": "device generator of libtdsfs (tdsfs_synth_genotypes): counter-based mix64 hash instead of Philox, "
                                     "normal approximation of the Balding-Nichols drift instead of a Beta draw (SURVEY 8(d) names Philox + Beta); "
                                     "same shape, frequency spectrum family, F = 0.05, 2 % missing; positions = cumsum of Geometric(1/50) gaps",
@@ -613,6 +619,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--snps", type=int, default=0, help="override the SNP count (profiling runs only; not a bench value)")
     ap.add_argument("--verify-windows", type=int, default=128, help="windows re-scored by the CPU oracle after the timed region")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every pass call by call instead of replaying the captured CUDA graph")
     ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config3 / ECB sub-records of the default N=1 run")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])

@@ -200,6 +200,13 @@ int tdsfs_run_bp(tdsfs_t* ctx, int32_t bg_mode, int64_t W, tdsfs_result_t* out, 
 int tdsfs_set_poisson_background(tdsfs_t* ctx, const double* q2d);
 int tdsfs_scan_poisson_bp(tdsfs_t* ctx, int64_t W, tdsfs_result_t* out, int64_t cap, int64_t* n_windows);
 
+/* One whole pass, asynchronous on the handle's stream: plan -> count kernel -> (peer exchange +) ln tables -> finish
+ * kernel, results left on the device (tdsfs_fetch_results), deferred errors in tdsfs_check.  Called repeatedly with the
+ * same arguments on device-resident data it captures the pass as a CUDA graph on the second call and replays it afterwards.
+ * With the peer exchange mapped (tdsfs_peer_import) the exchange is part of the pass: every rank calls it the same number
+ * of times. */
+int tdsfs_step_bp(tdsfs_t* ctx, int32_t bg_mode, int64_t W);
+
 /* Spectra of one scanned window (calculate_2d_sfs / calculate_1d_sfs on window_data): dense outputs, any NULL. */
 int tdsfs_window_spectra(tdsfs_t* ctx, int64_t window, uint64_t* sfs2d, uint64_t* sfs1d_p1, uint64_t* sfs1d_p2);
 

@@ -242,3 +242,41 @@ def test_fused_float_background(T, h):
         out[planned] = h.scan(20000)
         assert h.scan_info()[0] == planned
     assert_same(out[True], out[False])
+
+
+def test_step_bp_graph_replay_equals_run_bp(T, h):
+    """tdsfs_step_bp on device-resident data: eager, captured and replayed passes leave the same results as tdsfs_run_bp;
+    other arguments or a new load drop the graph."""
+    import torch
+    rng = np.random.default_rng(41)
+    n1, n2, S = 64, 64, 60000
+    G, w1, w2, pos, off = random_panel(rng, S, n1, n2, 3, 900000)
+    Gd, pd = torch.from_numpy(G.view(np.int32)).cuda(), torch.from_numpy(pos).cuda()
+    h.set_panel(n1, n2, True)
+    h.load_genotypes(Gd, S, w1, w2, n1, n2, pd, off)
+    ref = h.run_bp(T.BG_GENOME, 15000)
+    h.set_sync(False)
+    l0 = h.launch_count()
+    per_pass = []
+    for i in range(5):  # 1: eager, 2: capture + launch, 3..: replay
+        h.step_bp(T.BG_GENOME, 15000)
+        h.check()
+        per_pass.append(h.launch_count() - l0)
+        l0 = h.launch_count()
+        assert_same(h.fetch_results(len(ref["start"])), ref)
+    assert len(set(per_pass)) == 1, per_pass  # the replayed graph accounts for the same kernels as the eager pass
+    h.step_bp(T.BG_PER_CHROM, 15000)  # other arguments: eager again
+    h.check()
+    got = h.fetch_results(len(ref["start"]))
+    h.set_sync(True)
+    assert_same(got, h.run_bp(T.BG_PER_CHROM, 15000))
+    G2, w1, w2, pos2, off2 = random_panel(rng, S // 2, n1, n2, 2, 500000)
+    Gd2, pd2 = torch.from_numpy(G2.view(np.int32)).cuda(), torch.from_numpy(pos2).cuda()
+    h.load_genotypes(Gd2, S // 2, w1, w2, n1, n2, pd2, off2)  # new data: the old graph must not be replayed
+    h.set_sync(False)
+    for i in range(3):
+        h.step_bp(T.BG_GENOME, 15000)
+    h.check()
+    got = h.fetch_results(h.candidates(15000))
+    h.set_sync(True)
+    assert_same(got, h.run_bp(T.BG_GENOME, 15000))
