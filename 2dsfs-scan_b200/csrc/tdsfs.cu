@@ -37,6 +37,19 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// a rank that never arrives flags an error instead of hanging the others: ~60 s of SM cycles by default (ranks of a real job may
+// reach the exchange seconds apart), TDSFS_PEER_TIMEOUT_S overrides
+static long long peer_timeout_cycles() {
+  static long long v = 0;
+  if (!v) {
+    double s = 60.0;
+    if (const char* e = getenv("TDSFS_PEER_TIMEOUT_S")) s = std::max(0.001, atof(e));
+    v = (long long)(s * 2.0e9);
+  }
+  return v;
+}
+#define PEER_TIMEOUT_CYCLES peer_timeout_cycles()
+
 #define CK(call)                                                                                        \
   do {                                                                                                  \
     cudaError_t e__ = (call);                                                                           \
@@ -112,7 +125,9 @@ struct tdsfs_ctx {
   bool float_bg = false, tables_ready = false, fin_timed = false;
   bool poisson_bg = false;            // the tables hold ln q of a normalised background (tdsfs_set_poisson_background)
   double pq_n = 0, pq_sum = 0, pq_lnsum = 0;
-  bool tables_from_exchange = false;  // the merged exchange kernel already built the tables of this background
+  bool tables_from_exchange = false;  // the merged exchange kernel (or the count kernel's tail) already built the tables of this background
+  unsigned int* d_gridbar = nullptr;  // grid barrier of the count kernel's tail: arrivals, phase
+  bool want_tail_exchange = false;    // tdsfs_step_bp: the next tdsfs_background also exchanges the histogram (peer memory) in its tail
   bool x_timed = false;
   int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
   int* d_err = nullptr;
@@ -190,6 +205,7 @@ static bool is_device_ptr(const void* p) {
 // device-side error word -> return code (bit0 range, bit2 peer timeout, bit3 narrow-record overflow)
 static int deferred_error(tdsfs_ctx* c, int err) {
   if (err & 4) return fail(TDSFS_ERR_CUDA, "peer exchange: a rank did not reach the barrier in time; the background is incomplete");
+  if (err & 16) return fail(TDSFS_ERR_CUDA, "count kernel: its CTAs did not all reach the grid barrier in time; the background tables are incomplete");
   if (err & 1) return fail(TDSFS_ERR_RANGE, "an allele count exceeds 2n of the declared panel (n1=%d, n2=%d)", c->n1, c->n2);
   if (err & 8) {
     c->force_wide = true;
@@ -236,6 +252,8 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   k_ln_int_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_lnI, LN_TABLE);
   c->launches++;
   CK(cudaGetLastError());
+  CKR(dev_alloc(&c->d_gridbar, 2));
+  CK(cudaMemsetAsync(c->d_gridbar, 0, 2 * sizeof(unsigned int), c->stream));
   CKR(dev_alloc(&c->d_dxI, LN_TABLE));
   k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
   c->launches++;
@@ -306,7 +324,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
   dev_free(c->r_T1b); dev_free(c->r_flags); dev_free(c->d_scratch);
   for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  dev_free(c->d_dxI); dev_free(c->d_ws);
+  dev_free(c->d_dxI); dev_free(c->d_ws); dev_free(c->d_gridbar);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->plan_stream);
@@ -732,6 +750,30 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
         if (plain && c->W1 == 32 && c->W2 == 32) kern = k1_fused<32, 32, true>;        // 500 + 500 diploids (BASELINE config 5)
         else if (plain && c->W1 == 14 && c->W2 == 14) kern = k1_fused<14, 14, true>;   // 200 + 200 diploids (BASELINE config 4)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // Tail of the launch: a pass that is ONE launch over resident data (the usual case) also builds the ln tables of its
+        // background after a grid-wide barrier - and, inside tdsfs_step_bp with the peer exchange mapped, exchanges the
+        // histogram with the other ranks first - instead of leaving that to separate launches.
+        const bool one_launch = c->chunks.size() == 1 && !c->chunks[0].ev && c->chunks[0].r1 > c->chunks[0].r0;
+        const bool tail_x = c->want_tail_exchange && one_launch && mode != TDSFS_BG_NONE && NG == 1 && c->peer_ready &&
+                            c->d_hist == c->peer_exported_hist && c->gstride == c->peer_words;
+        const bool tail_fin = one_launch && mode != TDSFS_BG_NONE && !getenv("TDSFS_NO_TAIL") && (tail_x || !c->want_tail_exchange);
+        if (tail_fin) {
+          CKR(ensure_tables(c, NG));
+          q.tail = tail_x ? 2 : 1;
+          q.gridbar = c->d_gridbar;
+          q.tail_timeout = PEER_TIMEOUT_CYCLES;
+          FinParams& f = q.fin;
+          f.hist = c->d_hist; f.gstride = c->gstride; f.NG = NG; f.bins2d = c->bins2d; f.R1 = c->R1; f.R2 = c->R2;
+          f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum; f.B = c->d_B;
+          if (tail_x) {
+            for (int r = 0; r < PEER_MAX; ++r) { q.peer.hist[r] = c->peer_hist[r]; q.peer.flags[r] = c->peer_flags[r]; }
+            q.peer.rank = c->peer_rank; q.peer.world = c->peer_world; q.peer.words = c->peer_words; q.peer.err = c->d_err;
+            q.peer.timeout_cycles = PEER_TIMEOUT_CYCLES;
+            q.peer.ticket = reinterpret_cast<unsigned int*>(c->d_peer_flags + PEER_MAX);
+            q.epoch_mem = c->d_peer_flags + PEER_MAX + 1;
+            c->peer_epoch += 2;  // host mirror of the device epoch
+          }
+        }
         const long long tile_rows = (long long)p.tile_blocks * BLK;
         for (auto& ch : c->chunks) {
           if (ch.r1 <= ch.r0) continue;
@@ -747,6 +789,11 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
           c->fused_W = c->plan_W;
           c->fused_snp = c->plan_snp;
           c->ws_ready = true;
+        }
+        if (tail_fin) {
+          c->tables_ready = true;
+          c->tables_from_exchange = true;
+          c->fin_timed = false;
         }
       }
     }
@@ -784,6 +831,8 @@ extern "C" int tdsfs_background_device(tdsfs_t* c, void** dev_ptr, int64_t* n_wo
   if (!c || !c->keys_ready) return fail(TDSFS_ERR_STATE, "tdsfs_background first");
   CK(cudaSetDevice(c->device));
   CKR(peer_settle(c));
+  c->tables_ready = c->float_bg;  // the caller is about to change the histogram (all-reduce): integer tables are rebuilt by finalize
+  c->tables_from_exchange = false;
   if (dev_ptr) *dev_ptr = c->d_hist;
   if (n_words) *n_words = c->gstride * c->NG;
   if (n_groups) *n_groups = c->NG;
@@ -799,7 +848,7 @@ struct PeerBlob {  // TDSFS_PEER_BLOB_BYTES
 };
 static_assert(sizeof(PeerBlob) <= TDSFS_PEER_BLOB_BYTES, "blob size");
 
-constexpr long long PEER_TIMEOUT_CYCLES = 20LL * 1000 * 1000 * 1000;  // ~10 s: a rank that never arrives flags an error instead of hanging
+
 
 // Something other than the finalize kernel is about to touch the histogram: wait (on the stream) for the peers' pushes.
 static int peer_settle(tdsfs_ctx* c) {
@@ -911,6 +960,7 @@ extern "C" int tdsfs_peer_allreduce_background(tdsfs_t* c) {
   c->peer_pending = c->peer_epoch;
   CK(cudaGetLastError());
   c->tables_ready = false;
+  c->tables_from_exchange = false;
   return finish(c);
 }
 
@@ -1354,9 +1404,15 @@ extern "C" int tdsfs_run_bp(tdsfs_t* c, int32_t bg_mode, int64_t W, tdsfs_result
 // between dependent kernels shrink).  Results stay on the device (tdsfs_fetch_results); errors surface in tdsfs_check.
 static int step_eager(tdsfs_ctx* c, int32_t bg_mode, int64_t W) {
   CKR(plan(c, W, false));
-  CKR(tdsfs_background(c, bg_mode, 0, -1, -1));
-  if (c->peer_ready && c->NG == 1 && (bg_mode == TDSFS_BG_GENOME || bg_mode == TDSFS_BG_CHROM)) CKR(tdsfs_peer_reduce_finalize(c));
-  else CKR(tdsfs_finalize_background(c));
+  const bool exchange = c->peer_ready && (bg_mode == TDSFS_BG_GENOME || bg_mode == TDSFS_BG_CHROM);
+  c->want_tail_exchange = exchange;  // the count kernel's tail exchanges the histogram and builds the tables when it can
+  const int r = tdsfs_background(c, bg_mode, 0, -1, -1);
+  c->want_tail_exchange = false;
+  CKR(r);
+  if (!(c->tables_ready && c->tables_from_exchange)) {
+    if (exchange && c->NG == 1) CKR(tdsfs_peer_reduce_finalize(c));
+    else CKR(tdsfs_finalize_background(c));
+  }
   return scan(c, W, false, nullptr, 0, nullptr);
 }
 

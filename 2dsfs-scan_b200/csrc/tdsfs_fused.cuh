@@ -36,6 +36,14 @@ struct FusedParams {
   int tab_words;              // per-warp window tables: HASH_SLOTS + packed 1D words, a multiple of 4
   int nw1, nw2;               // packed 1D words per population: (n + 2) / 2
   int snap_nearest;           // range boundaries snap to the nearest window start (0: back to the start of the window that holds them)
+  // tail of the launch (single-launch passes only): after a grid-wide barrier the resident CTAs build the ln tables of the
+  // background themselves (1), after exchanging it with the other ranks through peer memory (2): no separate launches
+  int tail;
+  unsigned int* gridbar;
+  long long tail_timeout;
+  FinParams fin;
+  PeerParams peer;
+  unsigned long long* epoch_mem;
 };
 
 // dx[m] = (m+1) ln(m+1) - m ln m, written as ln(m+1) + m log1p(1/m) so that no large terms cancel
@@ -481,6 +489,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
   }
   __syncthreads();
   sink_flush(p, sm, cta_group, tid, blockDim.x);
+  if (q.tail) {
+    grid_barrier(q.gridbar, p.err, q.tail_timeout);  // every CTA's private histograms are in the global histogram
+    if (q.tail == 2) peer_exchange(q.peer, q.epoch_mem);
+    for (int g = 0; g < q.fin.NG; ++g) finalize_tables(q.fin, g, blockIdx.x, gridDim.x);
+    finalize_totals(q.fin, gridDim.x);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ finish pass

@@ -785,10 +785,8 @@ struct FinParams {
 
 __device__ __forceinline__ double ln_count(unsigned long long v) { return v ? log((double)v) : -INFINITY; }
 
-// ln tables and interior totals of background group g, by CTA `cta` of `ncta` (all of them must call: the last one to
-// arrive turns the totals into B and ln B)
-__device__ __forceinline__ void finalize_group(const FinParams& p, int g, int cta, int ncta, int ctas_total) {
-  __shared__ int s_last;
+// ln tables and interior totals of background group g, by CTA `cta` of the `ncta` CTAs that share the group
+__device__ __forceinline__ void finalize_tables(const FinParams& p, int g, int cta, int ncta) {
   const uint32_t* h = p.hist + (long long)g * p.gstride;
   unsigned long long local = 0;
   for (long long k = (long long)cta * blockDim.x + threadIdx.x; k < p.bins2d; k += (long long)ncta * blockDim.x) {
@@ -814,7 +812,12 @@ __device__ __forceinline__ void finalize_group(const FinParams& p, int g, int ct
       if ((threadIdx.x & 31) == 0 && loc) atomicAdd(p.Bsum + g * 3 + 1 + pop, loc);
     }
   }
-  // the last CTA to arrive turns the interior totals into the table [group][6] = B then ln B, and re-zeroes the sums
+}
+
+// every CTA that ran finalize_tables calls this once afterwards: the last one to arrive turns the interior totals of all groups
+// into the table [group][6] = B then ln B, and re-zeroes the sums
+__device__ __forceinline__ void finalize_totals(const FinParams& p, int ctas_total) {
+  __shared__ int s_last;
   __threadfence();
   __syncthreads();
   unsigned int* ticket = reinterpret_cast<unsigned int*>(p.Bsum + (long long)p.NG * 3);
@@ -836,7 +839,8 @@ __global__ void __launch_bounds__(256) k_finalize_counts(const __grid_constant__
     if ((int)threadIdx.x < p.wait_n) peer_wait(p.wait_flags + threadIdx.x, p.wait_epoch, p.err, p.timeout_cycles);
     __syncthreads();
   }
-  finalize_group(p, blockIdx.y, blockIdx.x, gridDim.x, gridDim.x * gridDim.y);
+  finalize_tables(p, blockIdx.y, blockIdx.x, gridDim.x);
+  finalize_totals(p, gridDim.x * gridDim.y);
 }
 
 // Multi-GPU, ONE launch per rank between the count kernel and the finish kernel: [barrier: every rank's count kernel is
@@ -850,10 +854,10 @@ struct PeerFinParams {
   unsigned long long* epoch_mem;  // [0] = last epoch used on this rank
 };
 
-__global__ void __launch_bounds__(256) k_peer_reduce_finalize(const __grid_constant__ PeerFinParams q) {
-  const PeerParams& p = q.x;
+// the exchange proper, by every CTA of a launch whose CTAs are all resident (they spin on the flags)
+__device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long long* epoch_mem) {
   __shared__ int s_last2;
-  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(q.epoch_mem) + 1;
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(epoch_mem) + 1;
   if ((int)threadIdx.x < p.world) {
     if (blockIdx.x == 0) {
       __threadfence_system();
@@ -897,14 +901,44 @@ __global__ void __launch_bounds__(256) k_peer_reduce_finalize(const __grid_const
   // second barrier: every rank's slice has landed in this rank's histogram
   if ((int)threadIdx.x < p.world) peer_wait(p.flags[p.rank] + threadIdx.x, e + 1, p.err, p.timeout_cycles);
   __syncthreads();
-  finalize_group(q.f, 0, blockIdx.x, gridDim.x, gridDim.x);
-  // the finalize ticket has seen every CTA: all of them read the epoch long ago.  One thread advances it and resets the
-  // reduce ticket for the next launch (the CTA that does it is the last one through finalize_group's ticket or any
-  // other: the writes only have to happen after every CTA's arrival at the first ticket, which the second barrier implies)
+  // every CTA has arrived at the ticket, so all of them read the epoch long ago: the last one advances it and resets the ticket
   if (s_last2 && threadIdx.x == 0) {
     *p.ticket = 0;
-    *q.epoch_mem = e + 1;
+    *epoch_mem = e + 1;
   }
+}
+
+__global__ void __launch_bounds__(256) k_peer_reduce_finalize(const __grid_constant__ PeerFinParams q) {
+  peer_exchange(q.x, q.epoch_mem);
+  finalize_tables(q.f, 0, blockIdx.x, gridDim.x);
+  finalize_totals(q.f, gridDim.x);
+}
+
+// Grid-wide barrier for launches whose CTAs are all resident (at most one CTA per SM): sense reversing, so the launch can be
+// replayed without resetting anything.  bar[0] = arrivals, bar[1] = phase.  A CTA that never arrives flags error bit 4 after
+// the timeout instead of hanging the others.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, int* err, long long timeout_cycles) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* phase = bar + 1;
+    const unsigned int old = *phase;  // read before arriving: the phase cannot advance without this CTA
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      *bar = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*phase == old) {
+        if (clock64() - t0 > timeout_cycles) {
+          atomicOr(err, 16);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
 }
 
 // precomputed (float) background: lb = ln b

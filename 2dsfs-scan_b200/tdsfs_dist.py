@@ -136,6 +136,11 @@ def allreduce_background(hist, group=None):
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        if hist.is_cuda:
+            # NCCL runs on torch's current stream, the library on its own: the tables must not be built from a histogram
+            # that is still being reduced (the caller's handle is synchronous, so the other direction is already ordered)
+            import torch
+            torch.cuda.current_stream(hist.device).synchronize()
     return hist
 
 

@@ -457,6 +457,7 @@ def measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, do_
             return h.run_bp(T.BG_GENOME, W, fetch=True)
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        barrier()  # rank 0 spent seconds in the oracle check above: the exchange kernels of the others must not wait for it
         res2 = e2e_step()
         barrier()
         t_c0 = time.time()

@@ -145,7 +145,7 @@ int tdsfs_background_device(tdsfs_t* ctx, void** dev_ptr, int64_t* n_words, int3
  *   per scan: tdsfs_background -> tdsfs_peer_allreduce_background -> tdsfs_finalize_background -> tdsfs_scan_*
  *   tdsfs_peer_close(ctx)                       on every rank BEFORE any rank changes its panel or is destroyed
  * tdsfs_peer_allreduce_background is asynchronous on the handle's stream; all ranks must call it the same number
- * of times.  A rank that never arrives makes the others flag TDSFS_ERR_CUDA (tdsfs_check) after ~10 s, not hang. */
+ * of times.  A rank that never arrives makes the others flag TDSFS_ERR_CUDA (tdsfs_check) after ~60 s (TDSFS_PEER_TIMEOUT_S), not hang. */
 #define TDSFS_PEER_BLOB_BYTES 192
 #define TDSFS_PEER_MAX_RANKS 16
 int tdsfs_peer_export(tdsfs_t* ctx, int32_t rank, int32_t world, void* blob);

@@ -66,6 +66,33 @@ def _worker(rank, world, port, out, peer=False):
         if use_peer:
             peer_teardown(h)
         results[name] = {k: v.tolist() for k, v in res.items()}
+    if peer:
+        # tdsfs_step_bp on device-resident shards: the exchange runs in the count kernel's tail (after a grid barrier), the whole
+        # pass is captured and replayed as a CUDA graph; every replay must leave the results of the call-by-call pass
+        plan = make_shard_plan(pos, off, world, W=20000)
+        pieces = plan[rank]
+        rows = np.concatenate([np.arange(p.lo, p.hi) for p in pieces])
+        G, w1, w2 = pack_codes(c1[rows], c2[rows])
+        Gd, pd = torch.from_numpy(G.view(np.int32)).to(dev), torch.from_numpy(pos[rows].astype(np.int32)).to(dev)
+        h.load_genotypes(Gd, len(rows), w1, w2, n1, n2, pd, local_offsets(pieces))
+        h.background(T.BG_GENOME)
+        assert peer_setup(h)
+        h.plan(20000)
+        h.background(T.BG_GENOME)
+        h.peer_reduce_finalize()
+        ref = h.scan(20000)
+        h.set_sync(False)
+        ok = True
+        for i in range(5):
+            h.step_bp(T.BG_GENOME, 20000)
+            h.check()
+            got = h.fetch_results(len(ref["start"]))
+            for k, v in ref.items():
+                same = np.allclose(got[k], v, rtol=1e-10, atol=1e-10, equal_nan=True) if v.dtype == np.float64 else np.array_equal(got[k], v)
+                ok = ok and bool(same)
+        h.set_sync(True)
+        peer_teardown(h)
+        out[f"step_ok_{rank}"] = ok
     if rank == 0:
         out["res"] = results
     dist.destroy_process_group()
@@ -89,6 +116,8 @@ def test_sharded_scan_equals_single_gpu(peer):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out, peer), nprocs=2, join=True)
+    if peer:
+        assert out["step_ok_0"] and out["step_ok_1"], "tdsfs_step_bp (exchange in the count kernel's tail, graph replay) differs from the call-by-call pass"
     n1, n2, sizes, c1, c2, pos, pack_codes = _panel()
     off = np.concatenate([[0], np.cumsum(sizes)])
     G, w1, w2 = pack_codes(c1, c2)
