@@ -756,7 +756,9 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
         const bool one_launch = c->chunks.size() == 1 && !c->chunks[0].ev && c->chunks[0].r1 > c->chunks[0].r0;
         const bool tail_x = c->want_tail_exchange && one_launch && mode != TDSFS_BG_NONE && NG == 1 && c->peer_ready &&
                             c->d_hist == c->peer_exported_hist && c->gstride == c->peer_words;
-        const bool tail_fin = one_launch && mode != TDSFS_BG_NONE && !getenv("TDSFS_NO_TAIL") && (tail_x || !c->want_tail_exchange);
+        // (measured: without an exchange the tail only matches the separate finalize launch of a replayed graph - off unless TDSFS_TAIL=1)
+        const bool tail_fin = one_launch && mode != TDSFS_BG_NONE && !getenv("TDSFS_NO_TAIL") &&
+                              (tail_x || (!c->want_tail_exchange && getenv("TDSFS_TAIL") != nullptr));
         if (tail_fin) {
           CKR(ensure_tables(c, NG));
           q.tail = tail_x ? 2 : 1;
