@@ -688,8 +688,9 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
       const int stage_stride = p.stage_bytes + p.tile_blocks * BLK * 4;
       const int fit = fit_for(p.tile_blocks, fuse);
       if (fit < 1) return fail(TDSFS_ERR_ARG, "row too wide for the count kernel's shared-memory ring");
-      p.cwarps = fuse ? std::min(fit, K1_CWARPS) : std::min(fit, std::max(4, std::min(K1_CWARPS, (128 * 1024) / p.stage_bytes)));
-      if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(K1_CWARPS, fit), atoi(e)));  // tuning knob
+      const int max_warps = (c->W1 == 32 && c->W2 == 32) ? k1f_max_warps<32, 32>() : K1_CWARPS;  // launch bound of the instantiation
+      p.cwarps = fuse ? std::min(fit, max_warps) : std::min(fit, std::max(4, std::min(max_warps, (128 * 1024) / p.stage_bytes)));
+      if (const char* e = getenv("TDSFS_K1_WARPS")) p.cwarps = std::max(1, std::min(std::min(max_warps, fit), atoi(e)));  // tuning knob
       int depth = 1;  // stages per warp
       if (const char* e = getenv("TDSFS_K1_DEPTH")) depth = std::max(1, atoi(e));  // tuning knob
       p.nstage = p.cwarps;

@@ -169,6 +169,45 @@ __device__ __forceinline__ int snap_row(const FusedParams& q, int t, bool& is_st
   return (fwd < 0 || (t - back) <= (fwd - t)) ? back : fwd;
 }
 
+// ---- population counts of one SNP from its bit planes (compile-time word counts)
+// sum of the popcounts of N words with carry-save adders: three words become a sum word (same weight) and a carry word (twice
+// the weight), level by level, until at most two words per weight are left - one POPC each.  N = 7: 3 adders + 4 POPC,
+// N = 16: 9 adders + 7 POPC (a POPC per word would be 16 of the slow pipe).
+template <int N>
+__device__ __forceinline__ uint32_t popc_sum(const uint32_t (&w)[N]) {
+  if constexpr (N == 1) {
+    return __popc(w[0]);
+  } else if constexpr (N == 2) {
+    return __popc(w[0]) + __popc(w[1]);
+  } else {
+    constexpr int M = N / 3, R = N - 3 * M;
+    uint32_t ones[M + R], twos[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) csa(twos[i], ones[i], w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) ones[M + i] = w[3 * M + i];
+    return popc_sum<M + R>(ones) + 2u * popc_sum<M>(twos);
+  }
+}
+
+// alt allele count and missing-call count of one population block (TW words = TW / 2 (lo, hi) pairs) of the lane's SNP:
+// codes 00, 01, 11, 10 = hom-ref, het, hom-alt, missing  =>  alt = popc(lo) + popc(lo & hi), missing = popc(hi) - popc(lo & hi).
+// Three bit-sliced counters over TW / 2 words each instead of one over all TW words plus one over the missing planes.
+template <int TW>
+__device__ __forceinline__ void count_pop_planes(const uint32_t* blk, uint32_t& alt, uint32_t& miss) {
+  constexpr int P = TW / 2;
+  uint32_t lo[P], hi[P], both[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    lo[i] = blk[(2 * i) * BLK];
+    hi[i] = blk[(2 * i + 1) * BLK];
+    both[i] = lo[i] & hi[i];
+  }
+  const uint32_t c = popc_sum<P>(both);
+  alt = popc_sum<P>(lo) + c;
+  miss = popc_sum<P>(hi) - c;
+}
+
 // folded bin of a raw alt count, 0 when it does not enter the 1D likelihood (same values as folded_interior, fewer instructions)
 __device__ __forceinline__ uint32_t fold_fast(int a, int n) {
   const uint32_t f = (uint32_t)min(a, 2 * n - a);
@@ -187,8 +226,13 @@ __device__ __forceinline__ void red_global_inc_if(bool pr, uint32_t* addr) {
 // background group for all rows (or none), no position restriction of the background, fold on, 4-byte records, no more
 // sample columns than the declared panel (so no count can leave the spectrum), 32 <= n <= 1023 (the privatised corner is
 // exactly 64 x 64 and every 1D bin is privatised).  Everything else takes the generic instantiation.
+// most warps an instantiation may be launched with: wide compile-time rows keep more words in registers and never fit more
+// than 16 warps beside their tiles and tables anyway
+template <int TW1, int TW2>
+constexpr int k1f_max_warps() { return (TW1 + TW2) >= 48 ? 16 : K1_CWARPS; }
+
 template <int TW1, int TW2, bool PLAIN>
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant__ FusedParams q) {
+__global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(const __grid_constant__ FusedParams q) {
   const KeyParams& p = q.k;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -376,8 +420,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_fused(const __grid_constant_
           int pv = 0;
           if (live) {
             const uint32_t* rowp = tile + (size_t)b * block_words + lane;
-            if (TW1 > 0 && TW1 == TW2) {
-              count_two_blocks_b32<TW1>(rowp, rowp + W1 * BLK, T1, M1, T2, M2);
+            if constexpr (TW1 > 0 && TW2 > 0) {  // T = alt + missing, as the generic counter returns it
+              count_pop_planes<TW1>(rowp, T1, M1);
+              count_pop_planes<TW2>(rowp + TW1 * BLK, T2, M2);
+              T1 += M1;
+              T2 += M2;
             } else {
               count_block_b32<TW1>(rowp, W1, T1, M1);
               count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);

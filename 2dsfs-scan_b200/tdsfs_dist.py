@@ -218,6 +218,8 @@ def _reduce_split_groups(handle, plan, rank, device, group=None):
     for j, c in enumerate(split):
         if c in mine and plan[rank]:
             hist[mine[c] * gstride:(mine[c] + 1) * gstride] = buf[j]
+    if hist.is_cuda:  # torch's stream wrote the sums back; the library's stream builds the tables next
+        torch.cuda.current_stream(hist.device).synchronize()
     return len(split)
 
 
