@@ -1544,7 +1544,9 @@ extern "C" int tdsfs_synth_genotypes(tdsfs_t* c, void* G_dev, int64_t S, int64_t
   if (!c || !G_dev || S < 0) return fail(TDSFS_ERR_ARG, "bad argument");
   if (!is_device_ptr(G_dev)) return fail(TDSFS_ERR_ARG, "G_dev must be device memory");
   CK(cudaSetDevice(c->device));
-  const long long total = S * (long long)(words1 + words2);
+  // every word of every 32-SNP block, padding rows included: in the block-transposed layout the words of the second population of
+  // a partial last block lie beyond S * RW (found by the bench line's cross-N checksums: they were left uninitialised)
+  const long long total = (S + BLK - 1) / BLK * BLK * (long long)(words1 + words2);
   const uint32_t thr = (uint32_t)(missing_rate * 65536.0);
   const long long blocks = (total + 255) / 256;
   if (blocks > 0x7FFFFFFFLL) return fail(TDSFS_ERR_ARG, "matrix too large for one launch");
