@@ -301,12 +301,17 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
       const int b_end = (r1 + BLK - 1) / BLK;  // blocks this launch may read (later ones may still be uploading)
       const int S4 = S & ~3;                   // positions below S4 come through TMA in whole 16-byte groups
       const int t_begin = slo / tile_rows, t_end = (shi - 1) / tile_rows + 1;
+      const int t_whole = min(b_end, S4 / BLK) / p.tile_blocks;  // tiles below this one are whole, positions included
+      const uint32_t gbytes_whole = (uint32_t)(p.tile_blocks * block_words * 4);
+      const uint32_t pbytes_whole = q.pos_tma ? (uint32_t)tile_rows * 4u : 0u;
       auto issue = [&](int t, int slot) {  // lane 0 only
         const int blk0 = t * p.tile_blocks;
-        const int nb = min(p.tile_blocks, b_end - blk0);
-        const uint32_t gbytes = (uint32_t)(nb * block_words * 4);
-        uint32_t pbytes = 0;
-        if (q.pos_tma) pbytes = (uint32_t)max(0, min(nb * BLK, S4 - blk0 * BLK)) * 4u;
+        uint32_t gbytes = gbytes_whole, pbytes = pbytes_whole;
+        if (t >= t_whole) {  // the last tile of the launch / of the matrix
+          const int nb = min(p.tile_blocks, b_end - blk0);
+          gbytes = (uint32_t)(nb * block_words * 4);
+          pbytes = q.pos_tma ? (uint32_t)max(0, min(nb * BLK, S4 - blk0 * BLK)) * 4u : 0u;
+        }
         uint8_t* stage = stages + (size_t)slot * stage_stride;
         mbar_arrive_expect_tx(bars + slot, gbytes + pbytes);
         bulk_g2s_stream(stage, p.G + (long long)blk0 * block_words, gbytes, bars + slot);
@@ -645,18 +650,18 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
     const uint32_t m1 = (1u << p.fmt.b1) - 1u, m2 = (1u << p.fmt.b2) - 1u, md = (1u << p.fmt.md) - 1u;
     const int sh2 = p.fmt.b1, shd1 = p.fmt.b1 + p.fmt.b2, shd2 = p.fmt.b1 + p.fmt.b2 + p.fmt.md;
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(p.rec);
-    // ln b of one decoded record: the three table reads
-    auto lookup = [&](uint32_t rr, double& l2, double& la, double& lb) {
+    // ln b of one decoded record: the 2D read (shared-memory corner, else a gather from the L2-resident table) ...
+    auto lookup2 = [&](uint32_t rr) -> double {
       const uint32_t k1 = rr & m1, k2 = (rr >> sh2) & m2;
-      const uint32_t a1 = k1 + 2u * ((rr >> shd1) & md), a2 = k2 + 2u * (rr >> shd2);
-      if ((k1 | k2) < (uint32_t)CORNER) {
-        l2 = s_c[(k1 << 6) | k2];
-      } else {
-        const uint32_t key = k1 * (uint32_t)p.C2 + k2;
-        l2 = key != last ? __ldg(p.lb2 + key) : 0.0;
-      }
-      la = s_a[a1];
-      lb = s_b[a2];
+      if ((k1 | k2) < (uint32_t)CORNER) return s_c[(k1 << 6) | k2];
+      const uint32_t key = k1 * (uint32_t)p.C2 + k2;
+      return key != last ? __ldg(p.lb2 + key) : 0.0;
+    };
+    // ... and the two 1D reads (shared memory)
+    auto lookup1 = [&](uint32_t rr, double& la, double& lb) {
+      const uint32_t k1 = rr & m1, k2 = (rr >> sh2) & m2;
+      la = s_a[k1 + 2u * ((rr >> shd1) & md)];
+      lb = s_b[k2 + 2u * (rr >> shd2)];
     };
     {
       // Windows dealt out round-robin; software pipeline over windows: while window i is processed, the first 256 records of
@@ -680,14 +685,18 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
       };
       double g2 = 0.0, g1a = 0.0, g1b = 0.0;
       auto consume = [&](const uint32_t (&r)[Q]) {
+        double l2[Q];  // all eight 2D reads first: the gathers that miss the corner come from L2 (~700 cycles) and overlap
 #pragma unroll
-        for (int h4 = 0; h4 < Q; h4 += 4) {
-          double l2[4], la[4], lb[4];
+        for (int j = 0; j < Q; ++j) l2[j] = lookup2(r[j]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) lookup(r[h4 + j], l2[j], la[j], lb[j]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
+        for (int j = 0; j < Q; ++j) {
+          double la, lb;
+          lookup1(r[j], la, lb);
+          g1a += la;
+          g1b += lb;
         }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) g2 += l2[j];
       };
       long long id = wid, nid = wid + nwarp;
       int lo, cnt, nlo, ncnt;

@@ -442,6 +442,6 @@ def test_capi_error_conventions(T, h):
 def test_panel_too_large_is_rejected(T, h):
     """(2 n1 + 1)(2 n2 + 1) must fit the 32-bit bin index: rejected with an argument error, no allocation attempted."""
     with pytest.raises(T.TdsfsError) as e:
-        h.set_panel(23171, 23171, True)   # 46343^2 = 2,147,673,649 > 2^31 - 1
+        h.set_panel(23170, 23170, True)   # 46341^2 = 2,147,488,281 > 2^31 - 1 = 2,147,483,647
     assert e.value.code == T.ERR_ARG
-    h.set_panel(23170, 23170, True)       # 46341^2 = 2,147,488,281 fits
+    h.set_panel(23169, 23169, True)       # 46339^2 = 2,147,302,921 fits
