@@ -685,18 +685,18 @@ __global__ void __launch_bounds__(256, 3) k3_finish(const __grid_constant__ Fini
       };
       double g2 = 0.0, g1a = 0.0, g1b = 0.0;
       auto consume = [&](const uint32_t (&r)[Q]) {
-        double l2[Q];  // all eight 2D reads first: the gathers that miss the corner come from L2 (~700 cycles) and overlap
+        // four records at a time: their reads are issued together, then accumulated (eight at a time measured 5 % slower)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) l2[j] = lookup2(r[j]);
+        for (int h4 = 0; h4 < Q; h4 += 4) {
+          double l2[4], la[4], lb[4];
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-          double la, lb;
-          lookup1(r[j], la, lb);
-          g1a += la;
-          g1b += lb;
+          for (int j = 0; j < 4; ++j) {
+            l2[j] = lookup2(r[h4 + j]);
+            lookup1(r[h4 + j], la[j], lb[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g2 += l2[j]; g1a += la[j]; g1b += lb[j]; }
         }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) g2 += l2[j];
       };
       long long id = wid, nid = wid + nwarp;
       int lo, cnt, nlo, ncnt;
