@@ -263,6 +263,9 @@ class LikelihoodInference_jointSFS:
         n2 = self.pop2_size if n2 is None else n2
         fl = self._flags(table) if flags is _UNSET else flags
         eng.load(table, n1, n2, self.fold if fold is None else fold, fl, cnt=cnt)
+        # window boundaries ahead of the count kernel (side stream); with a PackedPanel (genotype entry) this also arms the
+        # fused scan: the count kernel leaves every window's background-independent sums, one finish kernel scores them
+        eng.h.plan(size, snp_mode=snp_mode)
         if precomputed is None:
             eng.background(bg_mode, bg_chrom)
             eng.h.finalize_background()

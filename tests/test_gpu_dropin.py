@@ -184,10 +184,15 @@ def test_packed_panel_fast_path_equals_dict_path(mods):
         assert list(a) == list(b)
         for k in a:
             for f in a[k]:
-                assert close(a[k][f], b[k][f], 1e-11), (k, f, a[k][f], b[k][f])
+                assert close(a[k][f], b[k][f], 1e-10), (k, f, a[k][f], b[k][f])  # fused scan vs table scorer: different sum order
 
-    same(inst.combined_scan(P, 20000), inst.combined_scan(d, 20000))
-    same(inst.scan_perChr_bySNPs(P, 500), inst.scan_perChr_bySNPs(d, 500))
+    rp = inst.combined_scan(P, 20000)
+    assert inst._eng().h.scan_info() == (True, 4), "a PackedPanel scan must take the fused path with 4-byte records"
+    same(rp, inst.combined_scan(d, 20000))
+    assert inst._eng().h.scan_info()[0] is False  # the dict (counts) entry is scored by the table scorer
+    rp = inst.scan_perChr_bySNPs(P, 500)
+    assert inst._eng().h.scan_info()[0]
+    same(rp, inst.scan_perChr_bySNPs(d, 500))
     same(inst.scan_chooseChr(P, 500000, "NC_087088.1"), inst.scan_chooseChr(d, 500000, "NC_087088.1"))
     assert inst.calculate_2d_sfs(P) == inst.calculate_2d_sfs(d)
     assert inst.calculate_1d_sfs(P, "bv", 14, None, None, None) == inst.calculate_1d_sfs(d, "bv", 14, None, None, None)
