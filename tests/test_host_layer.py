@@ -102,3 +102,30 @@ def test_dictconv_c_path_equals_python_path():
             with pytest.raises(exc):
                 fn()
     assert E.SnpTable._from_dict_c(conv, {}, "a", "b").n == 0
+
+
+def test_bench_checksums_do_not_depend_on_the_sharding():
+    """bench.py's verify block: the order-independent checksums over all windows are the same however the windows are split
+    over ranks (that is what makes the N = 1 / 2 / 4 / 8 bench lines comparable)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rng = np.random.default_rng(2)
+    n = 5000
+    res = dict(chrom=rng.integers(0, 32, n).astype(np.int32), start=(1 + 20000 * rng.integers(0, 4000, n)).astype(np.int64),
+               snp_count=rng.integers(0, 700, n).astype(np.int32), n2d=rng.integers(0, 700, n).astype(np.int32),
+               n1d_p1=rng.integers(0, 700, n).astype(np.int32), n1d_p2=rng.integers(0, 700, n).astype(np.int32),
+               T2D=rng.normal(300, 50, n), T1D_p1=rng.normal(100, 20, n), T1D_p2=rng.normal(100, 20, n),
+               flags=np.where(rng.random(n) < 0.05, 8, np.where(rng.random(n) < 0.02, 1, 0)).astype(np.uint8))
+    res["snp_count"][res["flags"] == 8] = 0
+    whole = bench.result_checksums(res, res["chrom"].astype(np.int64), 8, (1, 2, 4))
+    for world in (2, 3, 8):
+        cuts = np.sort(rng.choice(np.arange(1, n), size=world - 1, replace=False))
+        parts = [bench.result_checksums({k: v[a:b] for k, v in res.items()}, res["chrom"][a:b].astype(np.int64), 8, (1, 2, 4))
+                 for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [n]]))]
+        tot = {k: sum(p[k] for p in parts) for k in whole}
+        tot["int_checksum"] %= 1 << 64
+        assert tot == whole
+    # and they do depend on the content
+    res["n2d"][17] += 1
+    assert bench.result_checksums(res, res["chrom"].astype(np.int64), 8, (1, 2, 4))["int_checksum"] != whole["int_checksum"]
