@@ -235,7 +235,10 @@ template <int TW1, int TW2, bool PLAIN>
 __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(const __grid_constant__ FusedParams q) {
   const KeyParams& p = q.k;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the warp index through a shuffle: the compiler then knows that everything derived from it (stage and barrier addresses,
+  // tile numbers, the TMA operands) is warp-uniform and keeps it in uniform registers instead of electing lanes around UBLKCP
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int W1 = TW1 > 0 ? TW1 : p.W1, W2 = TW2 > 0 ? TW2 : p.W2;
   const int RW = W1 + W2;
   const int tile_rows = p.tile_blocks * BLK;
@@ -294,6 +297,9 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
       if (shi <= lo_clamp) shi = lo_clamp;
       if (shi >= hi_clamp) shi = hi_clamp;
     }
+    slo = __shfl_sync(0xffffffffu, slo, 0);  // (uniform already; the shuffle tells the compiler)
+    shi = __shfl_sync(0xffffffffu, shi, 0);
+    st0 = __shfl_sync(0xffffffffu, (int)st0, 0) != 0;
     if (slo < shi) {
       uint8_t* stages = smem + (size_t)warp * depth * stage_stride;
       uint64_t* bars = full + warp * depth;
