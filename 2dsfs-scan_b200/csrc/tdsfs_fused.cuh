@@ -16,6 +16,8 @@
 //               that is its own background, a window with one populated bin) are re-scored per bin.  Windows larger than the
 //               warp tables (> WCAP SNPs) are scored by the CTA path over dense scratch in the same launch.
 #pragma once
+#include <type_traits>
+
 #include "tdsfs_kernels.cuh"
 
 namespace tdsfs {
@@ -416,17 +418,13 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
         aux += (key != 0 ? 1u << 10 : 0u) + (PLAIN ? 0u : cf << 20);
       };
 
-      for (int t = t_begin; t < t_end; ++t) {
-        const int blk0 = t * p.tile_blocks;
-        const int nb = min(p.tile_blocks, b_end - blk0);
-        mbar_wait(bars + slot, ph);
-        const uint8_t* stage = stages + (size_t)slot * stage_stride;
-        const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
-        const int* spos = reinterpret_cast<const int*>(stage + p.stage_bytes);
-        for (int b = 0; b < nb; ++b) {
+      // one 32-SNP block of the tile in the current stage.  INTERIOR (compile time) = the whole tile lies inside this warp's
+      // range, which is every tile but the first and the last: no per-block range tests, positions always from the stage
+      auto do_block = [&](auto interior_tag, int t, int blk0, int nb, int b, const uint32_t* tile, const int* spos) {
+          constexpr bool INTERIOR = decltype(interior_tag)::value;
           const int sb = (blk0 + b) * BLK;
           const int s = sb + lane;
-          const bool live = sb + BLK > slo && sb < shi;  // warp-uniform: the block holds rows of this warp's range
+          const bool live = INTERIOR || (sb + BLK > slo && sb < shi);  // warp-uniform: the block holds rows of this warp's range
           uint32_t T1 = 0, M1 = 0, T2 = 0, M2 = 0;
           int pv = 0;
           if (live) {
@@ -441,8 +439,8 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
             }
             if (q.wmode == 1) {
-              if (q.pos_tma && s < S4) pv = spos[b * BLK + lane];
-              else if (s < S) pv = __ldg(p.pos + s);
+              if (q.pos_tma && (INTERIOR || s < S4)) pv = spos[b * BLK + lane];
+              else if (INTERIOR || s < S) pv = __ldg(p.pos + s);
             }
           }
           if (b == nb - 1) {
@@ -454,8 +452,8 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               issue(t + depth, slot);
             }
           }
-          if (!live) continue;
-          const bool whole = sb >= slo && sb + BLK <= shi;  // every lane's row belongs to this warp
+          if (!live) return;
+          const bool whole = INTERIOR || (sb >= slo && sb + BLK <= shi);  // every lane's row belongs to this warp
           const bool act = whole || (s >= slo && s < shi);
           uint32_t key = 0, fa = 0, fb = 0, cf = 1;
           if (act) {
@@ -490,7 +488,7 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               if (p.flags) cf = (__ldg(p.flags + s) >> 1) & 1u;
             }
           }
-          if (!q.wmode) continue;
+          if (!q.wmode) return;
           // ---- window stage.  Fast path: every row of the block lies in the window the warp is already in
           if (whole && cur_id >= 0 && __all_sync(0xffffffffu, pv < win_end_pos && s < win_end_row)) {
             if (!overflow) {
@@ -498,7 +496,7 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               if (wcount > WCAP) overflow = true;
               else insert(key, fa, fb, cf);
             }
-            continue;
+            return;
           }
           int wid = -1;
           if (act) wid = window_id(q, s, pv, cw);
@@ -539,6 +537,19 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               win_end_row = c_lo + (cur_id - c_base + 1) * (int)q.W;
             }
           }
+      };
+
+      for (int t = t_begin; t < t_end; ++t) {
+        const int blk0 = t * p.tile_blocks;
+        const int nb = min(p.tile_blocks, b_end - blk0);
+        mbar_wait(bars + slot, ph);
+        const uint8_t* stage = stages + (size_t)slot * stage_stride;
+        const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+        const int* spos = reinterpret_cast<const int*>(stage + p.stage_bytes);
+        if (blk0 * BLK >= slo && (blk0 + nb) * BLK <= shi) {
+          for (int b = 0; b < nb; ++b) do_block(std::true_type{}, t, blk0, nb, b, tile, spos);
+        } else {
+          for (int b = 0; b < nb; ++b) do_block(std::false_type{}, t, blk0, nb, b, tile, spos);
         }
         if (++slot == depth) { slot = 0; ph ^= 1; }
       }
