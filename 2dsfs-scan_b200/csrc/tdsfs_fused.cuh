@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
         aux += (key != 0 ? 1u << 10 : 0u) + (PLAIN ? 0u : cf << 20);
       };
 
+      int pv_next = 0;  // position of this lane's row in the next block (the path without the positions in the TMA ring)
+      if (q.wmode == 1 && !q.pos_tma) {
+        const int s_first = t_begin * tile_rows + lane;
+        pv_next = s_first < S ? __ldg(p.pos + s_first) : 0;
+      }
       // one 32-SNP block of the tile in the current stage.  INTERIOR (compile time) = the whole tile lies inside this warp's
       // range, which is every tile but the first and the last: no per-block range tests, positions always from the stage
       auto do_block = [&](auto interior_tag, int t, int blk0, int nb, int b, const uint32_t* tile, const int* spos) {
@@ -438,10 +443,14 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
               count_block_b32<TW1>(rowp, W1, T1, M1);
               count_block_b32<TW2>(rowp + W1 * BLK, W2, T2, M2);
             }
-            if (q.wmode == 1) {
-              if (q.pos_tma && (INTERIOR || s < S4)) pv = spos[b * BLK + lane];
-              else if (INTERIOR || s < S) pv = __ldg(p.pos + s);
+            if (q.wmode == 1 && q.pos_tma) {
+              if (INTERIOR || s < S4) pv = spos[b * BLK + lane];
+              else if (s < S) pv = __ldg(p.pos + s);
             }
+          }
+          if (q.wmode == 1 && !q.pos_tma) {  // positions by plain loads, requested one block ahead (blocks come in row order)
+            pv = pv_next;
+            pv_next = s + BLK < S ? __ldg(p.pos + s + BLK) : 0;
           }
           if (b == nb - 1) {
             // the stage has been read completely: refill it BEFORE the fold / record / histogram / window work of its
