@@ -127,6 +127,7 @@ struct tdsfs_ctx {
   double pq_n = 0, pq_sum = 0, pq_lnsum = 0;
   bool tables_from_exchange = false;  // the merged exchange kernel (or the count kernel's tail) already built the tables of this background
   unsigned int* d_gridbar = nullptr;  // grid barrier of the count kernel's tail: arrivals, phase
+  unsigned long long* d_stamps = nullptr;  // diagnostics (TDSFS_TAIL_STAMPS=1): clock64 of CTA 0 at the phases of the tail
   bool want_tail_exchange = false;    // tdsfs_step_bp: the next tdsfs_background also exchanges the histogram (peer memory) in its tail
   bool x_timed = false;
   int score_group_warps = 1;  // warps per window in the shared-memory scorer (1, 2 or 4)
@@ -254,6 +255,10 @@ extern "C" int tdsfs_create(int device, tdsfs_t** out) {
   CK(cudaGetLastError());
   CKR(dev_alloc(&c->d_gridbar, 2));
   CK(cudaMemsetAsync(c->d_gridbar, 0, 2 * sizeof(unsigned int), c->stream));
+  if (getenv("TDSFS_TAIL_STAMPS")) {
+    CKR(dev_alloc(&c->d_stamps, 8));
+    CK(cudaMemsetAsync(c->d_stamps, 0, 8 * sizeof(unsigned long long), c->stream));
+  }
   CKR(dev_alloc(&c->d_dxI, LN_TABLE));
   k_dx_table<<<(LN_TABLE + 255) / 256, 256, 0, c->stream>>>(c->d_dxI, LN_TABLE);
   c->launches++;
@@ -324,7 +329,7 @@ extern "C" void tdsfs_destroy(tdsfs_t* c) {
   dev_free(c->r_count); dev_free(c->r_n2); dev_free(c->r_n1a); dev_free(c->r_n1b); dev_free(c->r_T2); dev_free(c->r_T1a);
   dev_free(c->r_T1b); dev_free(c->r_flags); dev_free(c->d_scratch);
   for (int i = 0; i < NEV; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  dev_free(c->d_dxI); dev_free(c->d_ws); dev_free(c->d_gridbar);
+  dev_free(c->d_dxI); dev_free(c->d_ws); dev_free(c->d_gridbar); dev_free(c->d_stamps);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->plan_stream);
@@ -765,6 +770,7 @@ extern "C" int tdsfs_background(tdsfs_t* c, int32_t mode, int32_t bg_chrom, int6
           q.tail = tail_x ? 2 : 1;
           q.gridbar = c->d_gridbar;
           q.tail_timeout = PEER_TIMEOUT_CYCLES;
+          q.stamps = c->d_stamps;
           FinParams& f = q.fin;
           f.hist = c->d_hist; f.gstride = c->gstride; f.NG = NG; f.bins2d = c->bins2d; f.R1 = c->R1; f.R2 = c->R2;
           f.n1 = c->n1; f.n2 = c->n2; f.lb2 = c->d_lb2; f.lb1a = c->d_lb1a; f.lb1b = c->d_lb1b; f.Bsum = c->d_Bsum; f.B = c->d_B;
@@ -1583,6 +1589,15 @@ extern "C" int tdsfs_timings(tdsfs_t* c, float* ms, int32_t n) {
 }
 
 extern "C" int64_t tdsfs_launch_count(tdsfs_t* c) { return c ? c->launches : 0; }
+
+extern "C" int tdsfs_tail_stamps(tdsfs_t* c, uint64_t* out8) {
+  if (!c || !out8) return fail(TDSFS_ERR_ARG, "ctx or out is NULL");
+  if (!c->d_stamps) return fail(TDSFS_ERR_STATE, "tail stamps are off (create the handle with TDSFS_TAIL_STAMPS=1 set)");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out8, c->d_stamps, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 extern "C" int tdsfs_scan_info(tdsfs_t* c, int32_t* fused, int32_t* record_bytes) {
   if (!c) return fail(TDSFS_ERR_ARG, "ctx is NULL");

@@ -46,6 +46,7 @@ struct FusedParams {
   FinParams fin;
   PeerParams peer;
   unsigned long long* epoch_mem;
+  unsigned long long* stamps;     // diagnostics: clock64 of CTA 0 at the phases of the tail (null = off)
 };
 
 // dx[m] = (m+1) ln(m+1) - m ln m, written as ln(m+1) + m log1p(1/m) so that no large terms cancel
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
   if (tid == 0) {
     for (int i = 0; i < p.nstage; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
+    if (q.stamps && blockIdx.x == 0) q.stamps[0] = (unsigned long long)clock64();
   }
   for (int i = tid; i < nhist; i += blockDim.x) sm.corner[i] = 0;
   if (q.wmode && warp < p.cwarps) {
@@ -568,10 +570,17 @@ __global__ void __launch_bounds__(k1f_max_warps<TW1, TW2>() * 32, 1) k1_fused(co
   __syncthreads();
   sink_flush(p, sm, cta_group, tid, blockDim.x);
   if (q.tail) {
+    // diagnostics (TDSFS_TAIL_STAMPS=1): clock64 of CTA 0 at [1] its histograms flushed, [2] past the grid barrier, [3..5] in
+    // peer_exchange, [6] ln tables done, [7] totals done ([0] = kernel entry)
+    auto stamp = [&](int i) { if (q.stamps && blockIdx.x == 0 && tid == 0) q.stamps[i] = (unsigned long long)clock64(); };
+    stamp(1);
     grid_barrier(q.gridbar, p.err, q.tail_timeout);  // every CTA's private histograms are in the global histogram
-    if (q.tail == 2) peer_exchange(q.peer, q.epoch_mem);
+    stamp(2);
+    if (q.tail == 2) peer_exchange(q.peer, q.epoch_mem, q.stamps);
     for (int g = 0; g < q.fin.NG; ++g) finalize_tables(q.fin, g, blockIdx.x, gridDim.x);
+    stamp(6);
     finalize_totals(q.fin, gridDim.x);
+    stamp(7);
   }
 }
 

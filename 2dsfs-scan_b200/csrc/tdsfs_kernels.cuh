@@ -789,10 +789,26 @@ __device__ __forceinline__ double ln_count(unsigned long long v) { return v ? lo
 __device__ __forceinline__ void finalize_tables(const FinParams& p, int g, int cta, int ncta) {
   const uint32_t* h = p.hist + (long long)g * p.gstride;
   unsigned long long local = 0;
-  for (long long k = (long long)cta * blockDim.x + threadIdx.x; k < p.bins2d; k += (long long)ncta * blockDim.x) {
-    const uint32_t v = h[k];
-    p.lb2[(long long)g * p.bins2d + k] = ln_count(v);
-    if (k > 0 && k < p.bins2d - 1) local += v;
+  // eight bins per thread and round, their loads issued together (in the count kernel's tail a thread has ~15 bins of a 1 M-bin
+  // spectrum, and a load per iteration made the loop a chain of L2 latencies)
+  constexpr int U = 8;
+  const long long stride = (long long)ncta * blockDim.x;
+  double* lb2 = p.lb2 + (long long)g * p.bins2d;
+  for (long long k = (long long)cta * blockDim.x + threadIdx.x; k < p.bins2d; k += U * stride) {
+    uint32_t v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long kk = k + u * stride;
+      v[u] = kk < p.bins2d ? __ldcg(h + kk) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long kk = k + u * stride;
+      if (kk < p.bins2d) {
+        lb2[kk] = ln_count(v[u]);
+        if (kk > 0 && kk < p.bins2d - 1) local += v[u];
+      }
+    }
   }
   for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.Bsum + g * 3, local);
@@ -855,8 +871,11 @@ struct PeerFinParams {
 };
 
 // the exchange proper, by every CTA of a launch whose CTAs are all resident (they spin on the flags)
-__device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long long* epoch_mem) {
+// `stamps` (diagnostics, normally null): CTA 0 leaves clock64 after barrier 1 [3], after its pushes are fenced [4] and after
+// barrier 2 [5]
+__device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long long* epoch_mem, unsigned long long* stamps = nullptr) {
   __shared__ int s_last2;
+  auto stamp = [&](int i) { if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[i] = (unsigned long long)clock64(); };
   const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(epoch_mem) + 1;
   if ((int)threadIdx.x < p.world) {
     if (blockIdx.x == 0) {
@@ -866,6 +885,7 @@ __device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long
     peer_wait(p.flags[p.rank] + threadIdx.x, e, p.err, p.timeout_cycles);
   }
   __syncthreads();
+  stamp(3);
   const long long n4 = p.words / 4;
   const long long lo = n4 * p.rank / p.world, hi = n4 * (p.rank + 1) / p.world;
   for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
@@ -892,6 +912,7 @@ __device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long
   // every thread's pushes are ordered before the CTA's ticket; the last CTA tells every rank that this rank is done
   __threadfence_system();
   __syncthreads();
+  stamp(4);
   if (threadIdx.x == 0) s_last2 = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (s_last2 && (int)threadIdx.x < p.world) {
@@ -901,6 +922,7 @@ __device__ __forceinline__ void peer_exchange(const PeerParams& p, unsigned long
   // second barrier: every rank's slice has landed in this rank's histogram
   if ((int)threadIdx.x < p.world) peer_wait(p.flags[p.rank] + threadIdx.x, e + 1, p.err, p.timeout_cycles);
   __syncthreads();
+  stamp(5);
   // every CTA has arrived at the ticket, so all of them read the epoch long ago: the last one advances it and resets the ticket
   if (s_last2 && threadIdx.x == 0) {
     *p.ticket = 0;

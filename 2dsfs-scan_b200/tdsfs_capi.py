@@ -21,7 +21,7 @@ EXPORTS = [
     "tdsfs_set_background", "tdsfs_finalize_background", "tdsfs_plan_bp", "tdsfs_plan_snp", "tdsfs_candidates_bp", "tdsfs_candidates_snp", "tdsfs_scan_bp",
     "tdsfs_scan_snp", "tdsfs_set_poisson_background", "tdsfs_scan_poisson_bp", "tdsfs_fetch_results", "tdsfs_check", "tdsfs_run_bp", "tdsfs_step_bp", "tdsfs_window_spectra", "tdsfs_likelihood",
     "tdsfs_poisson_score", "tdsfs_peer_export", "tdsfs_peer_import", "tdsfs_peer_allreduce_background", "tdsfs_peer_reduce_finalize", "tdsfs_peer_close",
-    "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_version",
+    "tdsfs_synth_genotypes", "tdsfs_timings", "tdsfs_launch_count", "tdsfs_scan_info", "tdsfs_tail_stamps", "tdsfs_version",
 ]
 
 
@@ -307,6 +307,12 @@ class Handle:
         f, b = C.c_int32(), C.c_int32()
         self._check(self._L.tdsfs_scan_info(self._h, C.byref(f), C.byref(b)))
         return bool(f.value), int(b.value)
+
+    def tail_stamps(self):
+        """Diagnostics (TDSFS_TAIL_STAMPS=1): SM-clock stamps of CTA 0 at the phases of the count kernel's tail (8 x uint64)."""
+        out = (C.c_uint64 * 8)()
+        self._check(self._L.tdsfs_tail_stamps(self._h, out))
+        return [int(x) for x in out]
 
     def check(self):
         """Synchronise and raise on deferred device-side errors (range, peer timeout, record overflow)."""

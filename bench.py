@@ -390,6 +390,12 @@ def measure_workload(args, cfg, h, T, torch, dist, dev, stream, world, rank, do_
     windows.append((t_a0, t_a1))
     h.check()
     fused, rec_bytes = h.scan_info()
+    if os.environ.get("TDSFS_TAIL_STAMPS"):  # diagnostics: phases of the count kernel's tail in the last step (SM cycles of CTA 0)
+        st = h.tail_stamps()
+        names = ("main loop + flush", "grid barrier", "peer barrier 1", "pull + push + fence", "peer barrier 2", "ln tables", "totals")
+        d = [st[i + 1] - st[i] for i in range(7)] if st[3] else [st[1] - st[0], st[2] - st[1], 0, 0, 0, st[6] - st[2], st[7] - st[6]]
+        print("[rank %d] tail stamps (us at 1965 MHz): " % rank + ", ".join("%s %.1f" % (n, c / 1965.0) for n, c in zip(names, d)),
+              file=sys.stderr, flush=True)
     ms_total = ev0.elapsed_time(ev1)
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:

@@ -234,6 +234,11 @@ int64_t tdsfs_launch_count(tdsfs_t* ctx); /* kernels launched by this handle so 
  * genotype-level entry: the count kernel leaves every window's background-independent sums and one finish kernel gathers
  * ln b over the per-SNP records), 0 for the table scorer; *record_bytes = 4 (narrow per-SNP record) or 8. */
 int tdsfs_scan_info(tdsfs_t* ctx, int32_t* fused, int32_t* record_bytes);
+/* Diagnostics (handles created with TDSFS_TAIL_STAMPS=1 in the environment, else TDSFS_ERR_STATE): SM clock (clock64) of
+ * CTA 0 of the last count kernel that ran a tail: [0] kernel entry, [1] its histograms flushed, [2] past the grid barrier,
+ * [3] past the first peer barrier, [4] its slice pushed and fenced, [5] past the second peer barrier, [6] ln tables written,
+ * [7] totals written.  No reference counterpart. */
+int tdsfs_tail_stamps(tdsfs_t* ctx, uint64_t* out8);
 int tdsfs_version(void);
 
 #ifdef __cplusplus
