@@ -789,26 +789,28 @@ __device__ __forceinline__ double ln_count(unsigned long long v) { return v ? lo
 __device__ __forceinline__ void finalize_tables(const FinParams& p, int g, int cta, int ncta) {
   const uint32_t* h = p.hist + (long long)g * p.gstride;
   unsigned long long local = 0;
-  // eight bins per thread and round, their loads issued together (in the count kernel's tail a thread has ~15 bins of a 1 M-bin
-  // spectrum, and a load per iteration made the loop a chain of L2 latencies)
-  constexpr int U = 8;
+  // four bins per thread and round, their loads issued together (in the count kernel's tail a thread has ~15 bins of a 1 M-bin
+  // spectrum, and a load per iteration made the loop a chain of L2 latencies: 9 us -> 6.5 us; eight per round with predicated
+  // slots measured no better than one)
+  constexpr int U = 4;
   const long long stride = (long long)ncta * blockDim.x;
   double* lb2 = p.lb2 + (long long)g * p.bins2d;
-  for (long long k = (long long)cta * blockDim.x + threadIdx.x; k < p.bins2d; k += U * stride) {
+  long long k = (long long)cta * blockDim.x + threadIdx.x;
+  for (; k + (U - 1) * stride < p.bins2d; k += U * stride) {
     uint32_t v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long kk = k + u * stride;
-      v[u] = kk < p.bins2d ? __ldcg(h + kk) : 0u;
-    }
+    for (int u = 0; u < U; ++u) v[u] = __ldcg(h + k + u * stride);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long kk = k + u * stride;
-      if (kk < p.bins2d) {
-        lb2[kk] = ln_count(v[u]);
-        if (kk > 0 && kk < p.bins2d - 1) local += v[u];
-      }
+      lb2[kk] = ln_count(v[u]);
+      if (kk > 0 && kk < p.bins2d - 1) local += v[u];
     }
+  }
+  for (; k < p.bins2d; k += stride) {
+    const uint32_t v = __ldcg(h + k);
+    lb2[k] = ln_count(v);
+    if (k > 0 && k < p.bins2d - 1) local += v;
   }
   for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.Bsum + g * 3, local);
